@@ -1,0 +1,133 @@
+/* triflow_b200 -- C ABI of the B200-native implicit method-of-lines hot path.
+ *
+ * The reference (celliern/triflow) is pure Python and has no FFI; these entry
+ * points are what its plugin points would bind for this path.  Each function
+ * cites the reference interface it replaces (paths relative to the reference
+ * repository).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions: every call returns 0 on success or a TF_E* code; the message of
+ * the last failure on the calling thread is tf_last_error().  Handles are
+ * opaque.  Host buffers are caller-owned plain double arrays; device buffers are
+ * library-owned.  One CUDA stream per context; calls on one context are not
+ * thread-safe, distinct contexts are independent.
+ */
+#ifndef TRIFLOW_B200_H
+#define TRIFLOW_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TF_OK 0
+#define TF_EINVAL 1   /* bad argument                                            */
+#define TF_ECUDA 2    /* CUDA runtime / driver error (see tf_last_error)         */
+#define TF_EMAXITER 3 /* adaptive step: internal iterations above max_iter       */
+#define TF_EDTMIN 4   /* adaptive step: internal time step below dt_min          */
+#define TF_ESINGULAR 5 /* zero / non-finite pivot in the banded factorisation    */
+
+typedef struct tf_ctx_s* tf_ctx_t;
+typedef struct tf_model_s* tf_model_t;
+typedef struct tf_state_s* tf_state_t;
+typedef struct tf_scheme_s* tf_scheme_t;
+
+/* Static description of a lowered model (produced by triflow_b200/codegen.py from
+ * the attributes a compiler plugin receives: core/model.py:244-291). */
+typedef struct {
+  int nvar;        /* model._nvar                                   */
+  int nhelp;       /* len(model._help_funcs)                        */
+  int half_width;  /* -model._bounds[0]                             */
+  int nnz;         /* len(model._J_sparse_array)                    */
+  int n_const;     /* host-evaluated uniform sub-expressions        */
+  int n_nodepar;   /* parameters passed as per-node arrays          */
+  int uses_x;      /* expressions reference the coordinate x        */
+  int chunk_nodes; /* nodes per thread the cubin was built for      */
+  int warps;       /* warps per CTA the cubin was built for         */
+} tf_model_desc;
+
+const char* tf_last_error(void);
+
+/* context = device + stream */
+int tf_ctx_create(int device, tf_ctx_t* out);
+int tf_ctx_destroy(tf_ctx_t ctx);
+int tf_ctx_sync(tf_ctx_t ctx);
+
+/* pinned host memory for upload / download buffers */
+int tf_host_alloc(size_t nbytes, void** out);
+int tf_host_free(void* p);
+
+/* Replaces numpy_compiler(model) -> (compute_F, compute_J)
+ * (core/compilers.py:181-224): loads the sm_100a cubin generated for the model. */
+int tf_model_load(tf_ctx_t ctx, const void* cubin, size_t nbytes, const tf_model_desc* desc,
+                  tf_model_t* out);
+int tf_model_unload(tf_model_t model);
+
+/* Device-resident fields of `batch` independent systems of n_nodes nodes.
+ * Replaces the per-call padding / view construction of init_computation_numpy
+ * (core/compilers.py:227-278). */
+int tf_state_create(tf_ctx_t ctx, tf_model_t model, int n_nodes, int batch, int periodic,
+                    tf_state_t* out);
+int tf_state_destroy(tf_state_t st);
+
+/* Upload host data; any pointer may be NULL (left unchanged).
+ *   x        [n_nodes]                       fields['x']
+ *   u        [batch][n_nodes*nvar]           BaseFields.uflat layout (core/fields.py:146-159)
+ *   helpers  [batch][nhelp][n_nodes]
+ *   nodepars [batch][n_nodepar][n_nodes]     array-valued parameters (core/routines.py:40)
+ *   consts   [batch][2*max(1,n_const)]       Lowered.uniform_table(...)                  */
+int tf_state_upload(tf_state_t st, const double* x, const double* u, const double* helpers,
+                    const double* nodepars, const double* consts);
+/* u [batch][n_nodes*nvar]: inverse of upload, BaseFields.fill order (core/fields.py:173-183) */
+int tf_state_download(tf_state_t st, double* u);
+
+/* F_Routine.__call__ -> compute_F_numpy (core/routines.py:37-45, compilers.py:281-289):
+ * out [batch][n_nodes*nvar]. */
+int tf_eval_F(tf_state_t st, double* out);
+/* J_Routine.__call__ -> compute_J_numpy (core/routines.py:82-91, compilers.py:292-301):
+ * out [batch][n_nodes][nnz], the per-node values of model._J_sparse_array; the
+ * caller places them in CSC with the reference's index rule (compilers.py:303-331). */
+int tf_eval_J(tf_state_t st, double* out);
+
+/* Rosenbrock-Wanner tableau (ROW_general.__init__, core/schemes.py:81-99).  Theta(theta)
+ * (core/schemes.py:518-559) is the one-stage tableau gamma=[[theta]], b=[1].
+ * alpha, gamma: [s][s] row-major; b: [s]; b_pred: [s] or NULL. */
+int tf_scheme_create(tf_ctx_t ctx, int s, const double* alpha, const double* gamma,
+                     const double* b, const double* b_pred, tf_scheme_t* out);
+int tf_scheme_destroy(tf_scheme_t sc);
+
+/* Declarative Dirichlet hook: U[var][0] = left, U[var][-1] = right, applied where the
+ * reference calls hook(t, fields, pars) (core/schemes.py:139,145,224,549,558). */
+int tf_hook_set_dirichlet(tf_state_t st, int var, int has_left, double left, int has_right,
+                          double right);
+int tf_hook_clear(tf_state_t st);
+
+/* n_steps fixed steps of ROW_general._fixed_step + post-hook (core/schemes.py:137-174)
+ * on every system.  err_out [batch] (or NULL): ||U_new - U_pred||_inf of the last step
+ * (NaN when the tableau has no b_pred). */
+int tf_scheme_step(tf_state_t st, tf_scheme_t sc, double dt, int n_steps, double* err_out);
+
+/* One call of ROW_general._variable_step (core/schemes.py:176-238) on a single system
+ * (batch == 1): embedded-error step-size control up to t + dt.
+ *   internal_dt  in/out, < 0 means "None" (first call starts at 1e-6)
+ *   max_iter / dt_min  <= 0 means "None"
+ *   n_fixed_steps out: number of _fixed_step evaluations performed            */
+int tf_scheme_advance(tf_state_t st, tf_scheme_t sc, double t, double dt, double tol,
+                      double safety_factor, int max_iter, double dt_min, int recompute_target,
+                      double* internal_dt, int* n_fixed_steps, double* last_err);
+
+/* status bits per system (bit0 bad pivot, bit1 singular border block) */
+int tf_state_status(tf_state_t st, int* status);
+/* number of kernels launched on this state's context since creation */
+long long tf_ctx_launch_count(tf_ctx_t ctx);
+/* CUDA-event timing on the context's stream: start/stop bracket, elapsed ms */
+int tf_ctx_timer_start(tf_ctx_t ctx);
+int tf_ctx_timer_stop(tf_ctx_t ctx, float* ms);
+/* per-kernel-family accumulated device time (ms) since the last reset; names out */
+int tf_ctx_profile(tf_ctx_t ctx, int enable);
+int tf_ctx_profile_read(tf_ctx_t ctx, int family, float* ms, long long* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,54 @@
+// Kernel parameter blocks shared by the model-specialised kernels
+// (tf_kernels.cuh, compiled per model to a cubin) and the host driver
+// (tf_host.cu, compiled once into libtriflow_b200.so).  Plain C structs.
+#pragma once
+
+#define TF_MAXS 6 /* max Rosenbrock stages (RODASPR) */
+
+struct TfGeom {
+  int N;        /* real nodes per system */
+  int nblk;     /* warp-blocks (32 chunks of M nodes) per system */
+  int tiles;    /* CTAs per system */
+  int batch;    /* systems */
+  int periodic;
+  int nhat;     /* interior unknowns (N - P) * V */
+};
+
+struct TfBuf {
+  double* U;            /* state                     [batch][nblk*C*32] */
+  double* Un;           /* next state (ping-pong) */
+  double* K[TF_MAXS];   /* stage vectors */
+  double* Y;            /* forward-substitution result */
+  double* H;            /* helper fields             [batch][NH][nblk*M*32] */
+  double* NP;           /* per-node parameters       [batch][NNODEPAR][nblk*M*32] */
+  double* X;            /* node coordinates          [nblk*M*32] */
+  double* cst;          /* uniform constants         [batch][2*max(1,NCONST)] */
+  double* Lf;           /* L multipliers             [batch][nblk*C*32*BETA] */
+  double* Uf;           /* U rows, pivot inverted    [batch][nblk*C*32*(BETA+1)] */
+  double* Wb;           /* border fill column L^-1 E [batch][nblk*C*32*NB] */
+  double* Gb;           /* border fill row F^T U^-1  [batch][nblk*C*32*NB] */
+  double* btab;         /* raw J of border couplings [batch][5][NB][NB] */
+  double* Sinv;         /* inverse border Schur complement [batch][NB][NB] */
+  double* xb;           /* border solution           [batch][NB] */
+  int* lead;            /* [batch][2] leading rows of W / G that may be non-zero */
+  int* status;          /* [batch] bit0: bad pivot, bit1: singular border block */
+  double* err;          /* [batch] embedded error estimate of the last step */
+  int* flags;           /* look-back: [0] ticket counter, then [batch*tiles] flags */
+  double* lbagg;        /* [batch*tiles][KMAX] tile aggregates */
+  double* lbinc;        /* [batch*tiles][KMAX] inclusive prefixes */
+};
+
+struct TfStage {
+  int nprev;               /* number of previous stage vectors used */
+  int istage;              /* index of the stage vector written */
+  double alpha[TF_MAXS];   /* U_i = U + sum alpha_j k_j */
+  double cfac[TF_MAXS];    /* gamma_ij / gamma_ii */
+  double dt;
+};
+
+struct TfUpdate {
+  int s;
+  int has_pred;
+  double b[TF_MAXS];
+  double bp[TF_MAXS];
+};
