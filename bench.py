@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the implicit method-of-lines hot path (BASELINE.json metric:
+implicit grid-point*steps/s; F+J+solve fraction of the HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W [--workload ensemble|ks|burgers|film]
+    python bench.py --impl reference ...        # CPU arm: the oracle port on host cores
+
+One "step" is one internal implicit step (one J build + factorisation + s stage
+solves + update) of every system in the batch.  Inputs are synthetic
+ and resident in HBM when the timed region starts; the timed
+region is bracketed by a barrier + stream synchronisation and timed with CUDA
+events on the launching stream, max over ranks.  Ensembles are sharded by member
+with no data-path collective (weak scaling: a fixed number of members per GPU).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from triflow_b200 import workloads as W  # noqa: E402
+
+# algorithmic bytes per node per internal step:
+#   Rosenbrock s stages: Q = 8[(1+s)B + (1+4s+s(s-1)/2)v + (1+s)n_a],  B = v^2 w
+#   (Theta is the 1-stage case of the same kernels: Q = 8[2B + 4v + n_a] in SURVEY;
+#    the kernels move the Rosenbrock s=1 traffic, 8[2B + 5v], we quote SURVEY's.)
+WORKLOADS = {
+    "ensemble": dict(v=1, w=3, s=3, Q=224, scheme="ROS3PRw", cfg="configs[4]"),
+    "burgers": dict(v=1, w=3, s=2, Q=152, scheme="ROS2", cfg="configs[1]"),
+    "ks": dict(v=1, w=5, s=3, Q=288, scheme="ROS3PRw", cfg="configs[2]"),
+    "film": dict(v=2, w=5, s=1, Q=384, scheme="Theta", cfg="configs[3]"),
+}
+
+
+def kernel_bytes(wk, family, stage=None):
+    """Algorithmic bytes per node of one launch of a kernel family: the SURVEY
+    §8d step model split over the launches (DESIGN.md 'Roofline accounting')."""
+    v, w, s = wk["v"], wk["w"], wk["s"]
+    B = v * v * w
+    if family == "factor":
+        return 8 * (B + v)                       # write factor, read U
+    lshare = B * (w // 2) / w                    # L part of the factor
+    if family == "fwd":                          # mean over stages
+        return 8 * (lshare + 2 * v + v * (s - 1) / 2)
+    if family == "bwd":
+        return 8 * ((B - lshare) + 2 * v)
+    return 0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown",
+                                  "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------- workloads
+def build_problem(name, members, N=None):
+    """Returns (model_name, scheme factory, x, fields, pars, hook, batch, N, dt)."""
+    from triflow_b200 import schemes as S
+    if name == "ensemble":
+        c = W.ensemble(N or 4096, members)
+        return ("advdiff", lambda m: S.ROS3PRw(m, time_stepping=False), c["x"], c["fields"],
+                c["pars"], S.Dirichlet(U=(1.0, 0.0)), len(c["members"]), c["x"].size, c["dt"])
+    if name == "ks":
+        c = W.kuramoto(N or 2 ** 20)
+        return ("ks", lambda m: S.ROS3PRw(m, time_stepping=False), c["x"], c["fields"],
+                c["pars"], S.null_hook, 1, c["x"].size, c["dt"])
+    if name == "burgers":
+        c = W.burgers(N or 2 ** 17, 1)
+        return ("burgers_up1", lambda m: S.ROS2(m), c["x"], c["fields"], c["pars"],
+                S.null_hook, 1, c["x"].size, c["dt"])
+    if name == "film":
+        c = W.film(N or 2 ** 18)
+        return ("film", lambda m: S.Theta(m, theta=1), c["x"], c["fields"], c["pars"],
+                S.null_hook, 1, c["x"].size, c["dt"])
+    raise SystemExit("unknown workload %r" % name)
+
+
+def run_gpu(args):
+    from triflow_b200 import _lib, distributed as D
+    from triflow_b200.ensemble import Ensemble
+    from triflow_b200.model import Model
+
+    rank, ws = D.init()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    wk = WORKLOADS[args.workload]
+    if args.workload == "ensemble":
+        per_gpu = args.members
+        lo = rank * per_gpu                     # weak scaling: per-GPU members fixed
+        members = (np.arange(lo, lo + per_gpu)) % (W.ENSEMBLE_K * W.ENSEMBLE_C)
+    else:
+        members = None                          # replicas only
+    mname, mk_scheme, x, fields, pars, hook, batch, N, dt = build_problem(
+        args.workload, members, args.nodes)
+    model = Model(**W.model_args(mname), compiler="cuda")
+    scheme = mk_scheme(model)
+    ens = Ensemble(model, scheme, x, fields, pars, hook=hook, batch=batch)
+    lib, ctx = _lib.lib(), model._cuda.ctx
+    units = float(N) * batch                    # nodes stepped per step on this rank
+
+    for _ in range(args.warmup):
+        ens.step(dt, 1)
+    ens.sync()
+    # -- timed region: K steps, state resident in HBM
+    launches0 = lib.tf_ctx_launch_count(ctx)
+    D.barrier()
+    ens.sync()
+    with ClockSampler(local) as clocks:
+        _lib.check(lib.tf_ctx_timer_start(ctx))
+        import ctypes
+        _lib.check(lib.tf_scheme_step(ens.state.h, scheme.handle, float(dt), args.steps, None))
+        ms = ctypes.c_float()
+        _lib.check(lib.tf_ctx_timer_stop(ctx, ctypes.byref(ms)))
+        ens.sync()
+    D.barrier()
+    launches = lib.tf_ctx_launch_count(ctx) - launches0
+    t_max = D.max_over_ranks(ms.value * 1e-3)
+    total_units = D.sum_over_ranks(units)
+    value = total_units * args.steps / t_max
+
+    # -- per-kernel device times (separate short pass, CUDA events per launch)
+    _lib.check(lib.tf_ctx_profile(ctx, 1))
+    psteps = max(1, min(args.steps, 5))
+    ens.step(dt, psteps)
+    fam = {}
+    for i, fname in enumerate(_lib.FAMILIES):
+        fms, fn = ctypes.c_float(), ctypes.c_longlong()
+        _lib.check(lib.tf_ctx_profile_read(ctx, i, ctypes.byref(fms), ctypes.byref(fn)))
+        if fn.value:
+            fam[fname] = (fms.value, fn.value)
+    _lib.check(lib.tf_ctx_profile(ctx, 0))
+    tot_ms = sum(v[0] for v in fam.values())
+    dom = max((f for f in fam if kernel_bytes(wk, f) > 0), key=lambda f: fam[f][0])
+    dom_ms, dom_n = fam[dom]
+    peak, peak_src = peaks()
+    achieved = kernel_bytes(wk, dom) * units / (dom_ms / dom_n * 1e-3) / 1e9
+    step_gbs = wk["Q"] * units * args.steps / (ms.value * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "tf_k_" + dom, "achieved": round(achieved, 1),
+                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peak_src,
+                "kernel_share_of_step": round(dom_ms / tot_ms, 3),
+                "step_achieved": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4),
+                "bytes_per_node_step": wk["Q"],
+                "family_ms_per_step": {k: round(v[0] / psteps, 4) for k, v in fam.items()}}
+
+    # -- end to end through the public API with host buffers (upload + step + download)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    nv = model._nvar
+    h_in = _lib.pinned_empty((batch, N * nv))
+    h_out = _lib.pinned_empty((batch, N * nv))
+    h_in[:] = ens.download()
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ens.upload(h_in)
+        ens.step(dt, 1)
+        ens.download(h_out)
+        h_in, h_out = h_out, h_in
+    t_e2e = D.max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": total_units * e2e_steps / t_e2e, "unit": "grid-point*steps/s",
+           "h2d_bytes_per_step": int(8 * N * nv * batch), "d2h_bytes_per_step": int(8 * N * nv * batch),
+           "steps": e2e_steps}
+    status = ens.state.status()
+    assert not status.any(), "factorisation failed in the bench"
+    assert np.isfinite(h_in).all(), "non-finite state after the bench"
+
+    cpu = None
+    if rank == 0 and ws == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args.workload, args.cpu_seconds)
+    if rank == 0:
+        out = {
+            "metric": "implicit grid-point*steps/s", "value": value,
+            "unit": "grid-point*steps/s", "n_gpus": ws, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_max * 1e3 / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (wk["cfg"], args.workload),
+                       "model": mname, "scheme": wk["scheme"], "nodes": N,
+                       "systems_per_gpu": batch, "dt": dt, "fixed_step": True,
+                       "parallelism": "members sharded x%d, no collective" % ws,
+                       "l2": "working set %.0f MB per GPU > 126 MB L2" % (
+                           units * wk["Q"] / 1e6) if units * wk["Q"] > 126e6 else
+                       "working set %.0f MB fits L2; no flush (steps are dependent)" % (
+                           units * wk["Q"] / 1e6)},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+
+
+# -------------------------------------------------------------- CPU baseline
+def _cpu_member(job):
+    name, r, N, steps = job
+    from oracle import schemes as O
+    from oracle.numpy_compiler import numpy_compiler
+    from triflow_b200.model import Model
+    c = W.ensemble(N, [r])
+    m = Model(**W.model_args("advdiff"), compiler=numpy_compiler)
+    pars = dict(k=float(c["pars"]["k"][0]), c=float(c["pars"]["c"][0]), periodic=False)
+    f = m.fields_template(x=c["x"], **c["fields"])
+    sch = O.ROS3PRw(m, time_stepping=False)
+    t0 = time.perf_counter()
+    t = 0.0
+    for _ in range(steps):
+        t, f = sch(t, f, c["dt"], pars, hook=W.readme_hook)
+    return time.perf_counter() - t0
+
+
+def cpu_rate(workload, budget_s, cores):
+    """Oracle port (numpy + SciPy SuperLU) of the same workload on host cores."""
+    from oracle import schemes as O
+    from oracle.numpy_compiler import numpy_compiler
+    from triflow_b200.model import Model
+    if workload == "ensemble":
+        import multiprocessing as mp
+        N, steps = 4096, 10
+        t0 = time.perf_counter()
+        _cpu_member(("advdiff", 0, N, 2))
+        per = (time.perf_counter() - t0) / 2
+        nmem = max(cores, int(budget_s / max(per * steps, 1e-3)) * cores)
+        nmem = min(nmem, 64 * cores)
+        jobs = [("advdiff", int(r), N, steps)
+                for r in np.linspace(0, W.ENSEMBLE_K * W.ENSEMBLE_C - 1, nmem)]
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_cpu_member, jobs)
+        wall = time.perf_counter() - t0
+        return (N * nmem * steps / wall,
+                "%d of 32768 members x %d steps over %d processes" % (nmem, steps, cores))
+    mk = {"ks": (W.kuramoto, "ks", lambda m: O.ROS3PRw(m, time_stepping=False)),
+          "burgers": (lambda N=None: W.burgers(N or 2 ** 17, 1), "burgers_up1", O.ROS2),
+          "film": (W.film, "film", lambda m: O.Theta(m, theta=1))}[workload]
+    c = mk[0]()
+    m = Model(**W.model_args(mk[1]), compiler=numpy_compiler)
+    f = m.fields_template(x=c["x"], **c["fields"])
+    sch = mk[2](m)
+    t, n, t0 = 0.0, 0, time.perf_counter()
+    while True:
+        t, f = sch(t, f, c["dt"], c["pars"])
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 20:
+            break
+    wall = time.perf_counter() - t0
+    return (c["x"].size * n / wall, "%d steps at full size N=%d, 1 process "
+            "(the path is single-threaded)" % (n, c["x"].size))
+
+
+def cpu_baseline(workload, budget_s):
+    cores = (os.cpu_count() or 1) if workload == "ensemble" else 1
+    v, sample = cpu_rate(workload, budget_s, cores)
+    return {"value": v, "unit": "grid-point*steps/s", "cores": cores, "kind": "port",
+            "sample": sample + "; rate extrapolated linearly"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wk = WORKLOADS[args.workload]
+    cores = (os.cpu_count() or 1) if args.workload == "ensemble" else 1
+    budget = max(2.0, min(25.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_rate(args.workload, 1.0, cores)
+    vals, sample = [], ""
+    for _ in range(max(1, min(args.steps, 3))):
+        v, sample = cpu_rate(args.workload, budget, cores)
+        vals.append(v)
+    v = float(np.mean(vals))
+    print(json.dumps({
+        "impl": "reference", "metric": "implicit grid-point*steps/s", "value": v,
+        "unit": "grid-point*steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (wk["cfg"], args.workload), "scheme": wk["scheme"]},
+        "cpu_baseline": {"value": v, "unit": "grid-point*steps/s", "cores": cores,
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "grid-point*steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ensemble", choices=sorted(WORKLOADS))
+    ap.add_argument("--members", type=int, default=W.ENSEMBLE_K * W.ENSEMBLE_C,
+                    help="ensemble members per GPU")
+    ap.add_argument("--nodes", type=int, default=None)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

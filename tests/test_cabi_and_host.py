@@ -1,0 +1,111 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol
+declared in include/triflow_b200.h; it fails loudly without a GPU; host logic
+(sharding, Dirichlet hook object, scheme tableaux)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from triflow_b200 import _lib
+    path = _lib.build_library()
+    L = ctypes.CDLL(path)
+    with open(os.path.join(ROOT, "include", "triflow_b200.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"\b(tf_[a-z_A-Z0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from triflow_b200 import _lib
+    h = ctypes.c_void_p()
+    rc = _lib.lib().tf_ctx_create(0, ctypes.byref(h))
+    assert rc == _lib.TF_ECUDA
+    assert b"no CPU fallback" in _lib.lib().tf_last_error()
+    from triflow_b200 import workloads as W
+    from triflow_b200.model import Model
+    m = Model(**W.model_args("heat"), compiler="cuda")      # lowering needs no GPU
+    x = np.linspace(0, 1, 50)
+    with pytest.raises(_lib.CudaUnavailable):
+        m.F(m.fields_template(x=x, T=x), dict(k=1, periodic=True))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "triflow_b200")):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+
+
+def test_shard_is_a_partition():
+    from triflow_b200.distributed import shard
+    for n, ws in [(32768, 8), (10, 3), (7, 8), (1, 1)]:
+        cuts = [shard(n, r, ws) for r in range(ws)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+
+
+def test_tableaux_match_oracle():
+    from oracle import schemes as O
+    from triflow_b200 import schemes as S
+    for name in ("ROS2", "ROS3PRw", "ROS3PRL", "RODASPR"):
+        a, g, b, bp = S.tableau(name)
+        oa, og, ob, obp = O._build(name)
+        assert np.array_equal(a, oa) and np.array_equal(g, og)
+        assert list(b) == list(ob)
+        assert (bp is None and obp is None) or list(bp) == list(obp)
+
+
+def test_dirichlet_hook_is_a_plain_hook_too():
+    from triflow_b200 import schemes as S
+    from triflow_b200.fields import BaseFields
+    f = BaseFields.factory1D(["U"], [])(x=np.arange(4.), U=np.zeros(4))
+    f2, p = S.Dirichlet(U=(1, None))(0.0, f, {})
+    assert f2["U"][0] == 1 and f2["U"][-1] == 0
+
+
+def test_two_rank_gloo_shard_and_gather():
+    """world_size 2 on CPU (gloo): sharded members gathered in member order."""
+    script = r'''
+import os, sys, numpy as np
+sys.path.insert(0, %r)
+from triflow_b200 import distributed as D
+rank, ws = D.init("gloo")
+lo, hi = D.shard(5, rank, ws)
+local = np.arange(lo, hi, dtype=float)[:, None] * np.ones((1, 3))
+D.barrier()
+full = D.gather_members(local, 5)
+mx = D.max_over_ranks(rank + 1.0)
+sm = D.sum_over_ranks(rank + 1.0)
+assert mx == 2.0 and sm == 3.0
+if rank == 0:
+    assert full.shape == (5, 3) and (full[:, 0] == np.arange(5)).all()
+    print("GATHER_OK")
+''' % ROOT
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29571")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29571", "-c", script] if False else
+                         [sys.executable, "-c",
+                          "import subprocess,sys,os;"
+                          "ps=[subprocess.Popen([sys.executable,'-c',%r],env=dict(os.environ,"
+                          "RANK=str(r),WORLD_SIZE='2',LOCAL_RANK=str(r)),stdout=subprocess.PIPE,"
+                          "text=True) for r in range(2)];"
+                          "outs=[p.communicate()[0] for p in ps];"
+                          "print(''.join(outs)); sys.exit(max(p.returncode for p in ps))" % script],
+                         env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GATHER_OK" in out.stdout

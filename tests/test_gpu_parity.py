@@ -1,0 +1,290 @@
+"""Parity tests proper (need a B200): the CUDA path, called through the plugin
+API / C-ABI, against (a) fixtures generated from the reference itself
+(tests/golden) and (b) the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): F, J <= 1e-12 relative (bit-exact is
+asserted wherever no libm pow is involved); trajectories <= 1e-8 relative to
+max|U - mean(U)| after the parity step counts of SURVEY.md §8d."""
+import numpy as np
+import pytest
+
+from helpers import csc_triplet, fj_tags, load_fj, model_name_of, rel_traj_err, traj
+
+pytestmark = pytest.mark.gpu
+
+TRAJ_TOL = 1e-8
+FX = dict(time_stepping=False)
+_GM, _OM = {}, {}
+
+
+def gmodel(name):
+    from triflow_b200 import workloads as W
+    from triflow_b200.model import Model
+    if name not in _GM:
+        _GM[name] = Model(**W.model_args(name), compiler="cuda")
+    return _GM[name]
+
+
+def omodel(name):
+    from oracle.numpy_compiler import numpy_compiler
+    from triflow_b200 import workloads as W
+    from triflow_b200.model import Model
+    if name not in _OM:
+        _OM[name] = Model(**W.model_args(name), compiler=numpy_compiler)
+    return _OM[name]
+
+
+def run_fixed(m, scheme, c, steps, every, hook=None, pars=None):
+    from triflow_b200 import schemes as S
+    f = m.fields_template(x=c["x"], **c["fields"])
+    pars = c["pars"] if pars is None else pars
+    t, snaps = 0.0, []
+    for i in range(steps):
+        t, f = scheme(t, f, c["dt"], pars, hook=hook or S.null_hook)
+        if (i + 1) % every == 0:
+            snaps.append(f.uflat.copy())
+    return np.array(snaps)
+
+
+# ------------------------------------------------------------------ F and J
+@pytest.mark.parametrize("tag", fj_tags())
+def test_F_J_vs_reference_golden(tag):
+    x, fields, pars, F_ref, J_ref = load_fj(tag)
+    m = gmodel(model_name_of(tag))
+    f = m.fields_template(x=x, **fields)
+    F = m.F(f, pars)
+    ip, ix, dat = csc_triplet(m.J(f, pars))
+    ipr, ixr, datr = csc_triplet(J_ref)
+    assert np.array_equal(ip, ipr) and np.array_equal(ix, ixr)
+    if "film" in tag:                                  # h**3 -> pow: <= 1 ulp
+        assert np.max(np.abs(F - F_ref)) <= 1e-12 * np.max(np.abs(F_ref))
+        assert np.max(np.abs(dat - datr)) <= 1e-12 * np.max(np.abs(datr))
+    else:
+        assert np.array_equal(F, F_ref)
+        assert np.array_equal(dat, datr)
+
+
+def test_dense_J_and_diff_approx():
+    """reference tests/test_model.py:21-50: J ~ brute-force finite differences."""
+    m = gmodel("heat")
+    x = np.linspace(0, 10, 100, endpoint=False)
+    f = m.fields_template(x=x, T=np.cos(x * 2 * np.pi / 10))
+    pars = dict(periodic=True, k=1)
+    Jd = m.J(f, pars, sparse=False)
+    Ja = m.F.diff_approx(f, pars)
+    assert np.isclose(Ja, Jd, rtol=1e-2, atol=1e-8).all()
+    assert np.isclose(Ja, m.J(f, pars).todense(), rtol=1e-2, atol=1e-8).all()
+
+
+# ------------------------------------------------------ cfg 1: README, N=200
+@pytest.mark.parametrize("sname,kw", [
+    ("ROS3PRw", FX), ("ROS2", {}), ("Theta", dict(theta=1)), ("Theta05", dict(theta=.5)),
+    ("ROS3PRL", FX), ("RODASPR", FX)])
+@pytest.mark.parametrize("hookkind", ["dirichlet", "python"])
+def test_readme_fixed(sname, kw, hookkind):
+    from triflow_b200 import schemes as S, workloads as W
+    c = W.readme(200)
+    m = gmodel("advdiff")
+    cls = getattr(S, "Theta" if sname.startswith("Theta") else sname)
+    hook = S.Dirichlet(U=(1, 0)) if hookkind == "dirichlet" else W.readme_hook
+    snaps = run_fixed(m, cls(m, **kw), c, 5, 1, hook=hook)
+    assert rel_traj_err(snaps, traj()["readme_fixed_" + sname]) <= TRAJ_TOL
+
+
+@pytest.mark.parametrize("hookkind", ["dirichlet", "python"])
+def test_readme_adaptive_controller(hookkind):
+    """Own controller of ROS3PRw (schemes.py:176-238): same internal step counts
+    as the reference and the same trajectory."""
+    from triflow_b200 import schemes as S, workloads as W
+    g = traj()
+    c = W.readme(200)
+    m = gmodel("advdiff")
+    sch = S.ROS3PRw(m, tol=1e-1)
+    hook = S.Dirichlet(U=(1, 0)) if hookkind == "dirichlet" else W.readme_hook
+    f = m.fields_template(x=c["x"], **c["fields"])
+    t, snaps, counts = 0.0, [], []
+    for _ in range(5):
+        n0 = sch.n_fixed_steps
+        f, _p = W.readme_hook(t, f, c["pars"])
+        t, f = sch(t, f, c["dt"], c["pars"], hook=hook)
+        snaps.append(f.uflat.copy())
+        counts.append(sch.n_fixed_steps - n0)
+    assert counts == [55, 10, 13, 14, 10]
+    assert rel_traj_err(np.array(snaps), g["readme_adaptive_ROS3PRw"]) <= TRAJ_TOL
+    assert abs(snaps[-1].sum() - 16.7597312006418) < 1e-8
+
+
+def test_readme_through_simulation():
+    """Simulation default (double wrapped, simulation.py:190-197) and fixed."""
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.simulation import Simulation
+    g = traj()
+    c = W.readme(200)
+    m = gmodel("advdiff")
+    sim = Simulation(m, dict(x=c["x"], **c["fields"]), c["pars"], dt=c["dt"],
+                     tmax=c["tmax"], hook=W.readme_hook, scheme=S.ROS3PRw,
+                     time_stepping=False)
+    snaps = np.array([f.uflat.copy() for _, f in sim])
+    assert sim.t == 2.5 and sim.status == "finished"
+    assert rel_traj_err(snaps, g["readme_simfixed_ROS3PRw"]) <= TRAJ_TOL
+    sim = Simulation(m, dict(x=c["x"], **c["fields"]), c["pars"], dt=c["dt"],
+                     tmax=c["tmax"], hook=S.Dirichlet(U=(1, 0)), scheme=S.ROS3PRw)
+    snaps = np.array([f.uflat.copy() for _, f in sim])
+    assert rel_traj_err(snaps, g["readme_simdefault_ROS3PRw"]) <= 1e-7
+    assert abs(snaps[-1].sum() - 16.777160348256707) < 1e-6
+
+
+def test_runtime_errors_like_reference():
+    """reference tests/test_simulation.py:61-77."""
+    from triflow_b200 import schemes as S
+    m = gmodel("heat")
+    x = np.linspace(0, 10, 50, endpoint=False)
+    f = m.fields_template(x=x, T=np.cos(x * 2 * np.pi / 10))
+    pars = dict(periodic=True, k=1)
+    with pytest.raises(RuntimeError):
+        S.ROS3PRw(m, tol=1e-1, max_iter=2)(0.0, f, 1.0, pars)
+    with pytest.raises(RuntimeError):
+        S.ROS3PRw(m, tol=1e-1, dt_min=.1)(0.0, f, 1.0, pars)
+
+
+@pytest.mark.parametrize("sname", ["ROS2", "ROS3PRL", "ROS3PRw", "RODASPR", "Theta"])
+def test_heat_equation_decays(sname):
+    """reference tests/test_simulation.py:20-35 (mean stays 0, t reaches tmax)."""
+    from triflow_b200 import schemes as S
+    from triflow_b200.simulation import Simulation
+    m = gmodel("heat")
+    x = np.linspace(0, 10, 50, endpoint=False)
+    sim = Simulation(m, dict(x=x, T=np.cos(x * 2 * np.pi / 10)), dict(periodic=True, k=1),
+                     scheme=getattr(S, sname), dt=1, tmax=20, tol=1e-1)
+    for t, fields in sim:
+        pass
+    assert t == 20
+    assert np.isclose(fields["T"].values.mean(), 0, atol=1e-9)
+
+
+@pytest.mark.parametrize("sname,kw", [("ROS2", {}), ("ROS3PRw", FX), ("Theta", {})])
+def test_heat50_golden(sname, kw):
+    from triflow_b200 import schemes as S
+    x = np.linspace(0, 10, 50, endpoint=False)
+    c = dict(x=x, fields=dict(T=np.cos(x * 2 * np.pi / 10)),
+             pars=dict(k=1, periodic=True), dt=1.0)
+    m = gmodel("heat")
+    snaps = run_fixed(m, getattr(S, sname)(m, **kw), c, 20, 5)
+    assert rel_traj_err(snaps, traj()["heat50_" + sname]) <= TRAJ_TOL
+
+
+# ------------------------------------------------------------- cfg 2, 3, 4
+@pytest.mark.parametrize("acc", [1, 2])
+def test_burgers_golden(acc):
+    from triflow_b200 import schemes as S, workloads as W
+    c = W.burgers(2048, acc)
+    m = gmodel(c["model"])
+    snaps = run_fixed(m, S.ROS2(m), c, 50, 10)
+    assert rel_traj_err(snaps, traj()["burgers_up%d_2048" % acc]) <= TRAJ_TOL
+
+
+@pytest.mark.parametrize("N", [2048, 1000])
+def test_ks_golden(N):
+    from triflow_b200 import schemes as S, workloads as W
+    c = W.kuramoto(N)
+    m = gmodel("ks")
+    snaps = run_fixed(m, S.ROS3PRw(m, **FX), c, 50, 10)
+    assert rel_traj_err(snaps, traj()["ks_%d" % N]) <= TRAJ_TOL
+
+
+def test_ks_edge_golden():
+    from triflow_b200 import schemes as S, workloads as W
+    c = W.kuramoto(512)
+    m = gmodel("ks")
+    snaps = run_fixed(m, S.ROS3PRw(m, **FX), c, 20, 5, pars=dict(periodic=False))
+    assert rel_traj_err(snaps, traj()["ks_512_edge"]) <= TRAJ_TOL
+
+
+@pytest.mark.parametrize("theta", [1, .5])
+def test_film_golden(theta):
+    from triflow_b200 import schemes as S, workloads as W
+    c = W.film(1024, theta)
+    m = gmodel("film")
+    snaps = run_fixed(m, S.Theta(m, theta=theta), c, 100, 20)
+    assert rel_traj_err(snaps, traj()["film_1024_theta%g" % theta]) <= TRAJ_TOL
+
+
+@pytest.mark.parametrize("name,N,scheme,kw,steps", [
+    ("ks", 70001, "ROS3PRw", FX, 3), ("burgers_up1", 131072, "ROS2", {}, 3),
+    ("burgers_up3", 5000, "ROS2", {}, 3), ("kdv", 3000, "ROS3PRL", FX, 3),
+    ("coupled", 777, "ROS3PRw", FX, 3), ("helper_dx", 400, "Theta", {}, 3)])
+@pytest.mark.parametrize("periodic", [True, False])
+def test_steps_vs_oracle_many_tiles(name, N, scheme, kw, steps, periodic):
+    """Several look-back tiles, ragged N, both boundary kinds, vs the oracle."""
+    from oracle import schemes as O
+    from triflow_b200 import schemes as S
+    rng = np.random.default_rng(N)
+    gm, om = gmodel(name), omodel(name)
+    x = np.arange(N) * 0.2
+    fields = {v: 1 + 0.3 * np.sin(2 * np.pi * 7 * x / x[-1]) + 1e-2 * rng.standard_normal(N)
+              for v in [*gm._dep_vars, *gm._help_funcs]}
+    pars = {p: 0.1 + 0.05 * i for i, p in enumerate(gm._pars)}
+    pars["periodic"] = periodic
+    c = dict(x=x, fields=fields, pars=pars, dt=0.05)
+    sg = run_fixed(gm, getattr(S, scheme)(gm, **kw), c, steps, steps)
+    f = om.fields_template(x=x, **fields)
+    t = 0.0
+    sch = getattr(O, scheme)(om, **kw)
+    for _ in range(steps):
+        t, f = sch(t, f, 0.05, pars)
+    assert rel_traj_err(sg[-1], f.uflat) <= TRAJ_TOL
+
+
+# ------------------------------------------------------------ cfg 5 ensemble
+def test_ensemble_members_golden():
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.ensemble import Ensemble
+    g = traj()
+    mem = g["ensemble_512_members"]
+    c = W.ensemble(512, mem)
+    m = gmodel("advdiff")
+    ens = Ensemble(m, S.ROS3PRw(m, **FX), c["x"], c["fields"], c["pars"],
+                   hook=S.Dirichlet(U=(1.0, 0.0)), batch=len(mem))
+    ens.step(c["dt"], 100)
+    U = ens.download()
+    for idx in range(len(mem)):
+        assert rel_traj_err(U[idx], g["ensemble_512_final"][idx]) <= TRAJ_TOL
+
+
+def test_ensemble_full_size_properties():
+    """N=4096 members at full grid size: every member equals the same member run
+    alone (independence), and members with equal parameters agree bit-for-bit."""
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.ensemble import Ensemble
+    mem = np.array([0, 127, 16384, 32767, 127, 5000])
+    c = W.ensemble(4096, mem)
+    m = gmodel("advdiff")
+    ens = Ensemble(m, S.ROS3PRw(m, **FX), c["x"], c["fields"], c["pars"],
+                   hook=S.Dirichlet(U=(1.0, 0.0)), batch=len(mem))
+    ens.step(c["dt"], 10)
+    U = ens.download()
+    assert np.array_equal(U[1], U[4])
+    assert np.isfinite(U).all()
+    sch = S.ROS3PRw(m, **FX)
+    pars = dict(k=float(c["pars"]["k"][2]), c=float(c["pars"]["c"][2]), periodic=False)
+    f = m.fields_template(x=c["x"], **c["fields"])
+    _, f = sch.run_fixed(0.0, f, c["dt"], 10, pars, hook=S.Dirichlet(U=(1.0, 0.0)))
+    assert np.array_equal(f.uflat, U[2])
+
+
+# -------------------------------------------- full-size, size-independent checks
+def test_ks_full_size_linear_solve_residual():
+    """N = 2^20: one backward-Euler step U1 = U0 + A^-1 dt F(U0) must satisfy
+    (I - dt J(U0)) (U1 - U0) = dt F(U0) with F, J evaluated by the (golden-pinned)
+    eval kernels -> residual check of factor + sweeps at full size."""
+    from triflow_b200 import schemes as S, workloads as W
+    c = W.kuramoto(2 ** 20)
+    m = gmodel("ks")
+    f0 = m.fields_template(x=c["x"], **c["fields"])
+    dt = c["dt"]
+    _, f1 = S.Theta(m, theta=1)(0.0, f0, dt, c["pars"])
+    F0 = m.F(f0, c["pars"])
+    J0 = m.J(f0, c["pars"])
+    d = f1.uflat - f0.uflat
+    res = d - dt * (J0 @ d) - dt * F0
+    assert np.max(np.abs(res)) <= 1e-9 * np.max(np.abs(dt * F0))

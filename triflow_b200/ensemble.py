@@ -1,0 +1,73 @@
+"""Parameter-sweep ensembles: many independent systems stepped together.
+
+The reference has no batch API (one ``Model`` + scheme run per parameter set,
+SURVEY.md §8d cfg 5); here ``batch`` systems share a grid and a model and differ
+in initial state and/or parameter values.  Each system is an independent banded
+problem (one CTA tile chain per system), so an ensemble shards across GPUs with
+no data-path communication (:mod:`triflow_b200.distributed`).
+"""
+
+import numpy as np
+
+from . import _lib
+from .schemes import Dirichlet, null_hook
+
+
+class Ensemble:
+    """``batch`` systems of one model on one device.
+
+    ``fields``: dict name -> ``(N,)`` (shared) or ``(batch, N)``.
+    ``pars``: dict name -> scalar, ``(batch,)`` (one value per member), ``(N,)``
+    or ``(batch, N)`` (per-node arrays), plus ``periodic``.
+    ``scheme``: a scheme instance from :mod:`triflow_b200.schemes` (its tableau is
+    used; stepping is fixed-step).
+    """
+
+    def __init__(self, model, scheme, x, fields, pars, hook=null_hook, batch=None):
+        self.model, self.scheme = model, scheme
+        cm = model._cuda
+        x = np.asarray(x, dtype=np.float64)
+        N = x.size
+        if batch is None:
+            batch = 1
+            for v in list(fields.values()) + [pars[p] for p in model._pars]:
+                if np.ndim(v) == 2 or (np.ndim(v) == 1 and np.shape(v)[0] != N):
+                    batch = max(batch, np.shape(v)[0])
+        self.batch, self.N = int(batch), N
+        self.nvar = model._nvar
+        self.pars = dict(pars)
+        self.state = cm.new_state(pars, N, self.batch, bool(pars["periodic"]))
+        named = {h: fields[h] for h in model._help_funcs}
+        self.state.set_inputs(x, named, pars)
+        u = np.stack([np.broadcast_to(np.asarray(fields[v], dtype=np.float64),
+                                      (self.batch, N)) for v in model._dep_vars], axis=2)
+        self.state.upload(u=u.reshape(self.batch, N * self.nvar))
+        if not scheme._on_device(hook):
+            raise ValueError("ensembles take declarative hooks (schemes.Dirichlet) only")
+        scheme._set_hook(self.state, hook)
+        self.t = 0.0
+
+    def upload(self, u):
+        """``u``: (batch, N*nvar) in uflat layout."""
+        self.state.upload(u=np.asarray(u).reshape(self.batch, self.N * self.nvar))
+
+    def step(self, dt, n_steps=1, want_err=False):
+        err = np.empty(self.batch) if want_err else None
+        _lib.check(_lib.lib().tf_scheme_step(self.state.h, self.scheme.handle, float(dt),
+                                             int(n_steps), _lib.dptr(err)))
+        self.t += n_steps * dt
+        return err
+
+    def download(self, out=None):
+        return self.state.download(out)
+
+    def member_fields(self, r, u=None):
+        u = self.download() if u is None else u
+        cols = u[r].reshape(self.N, self.nvar)
+        return {v: cols[:, e].copy() for e, v in enumerate(self.model._dep_vars)}
+
+    def sync(self):
+        _lib.check(_lib.lib().tf_ctx_sync(self.state.cmodel.ctx))
+
+
+__all__ = ["Ensemble", "Dirichlet"]
