@@ -30,7 +30,7 @@ extern "C" void run(int N, int periodic, const double* fields, const double* npa
     for (int q = 0; q < TF_NNODEPAR; ++q) in.np[q] = npar[q * N + i];
     in.x = x[i];
     double f[TF_NVAR]; double jv[TF_NNZ];
-    tf_model_F(cst, in, f); tf_model_J(cst, in, jv);
+    tf_model_F<TF_FAST_DIV != 0>(cst, in, f); tf_model_J<TF_FAST_DIV != 0>(cst, in, jv);
     for (int e = 0; e < TF_NVAR; ++e) F[i * TF_NVAR + e] = f[e];
     for (int k = 0; k < TF_NNZ; ++k) J[i * TF_NNZ + k] = jv[k];
   }

@@ -74,7 +74,8 @@ def build_cubin(header, chunk_nodes, warps, fast_div=False):
     """Compile a generated model header + tf_kernels.cuh to an sm_100a cubin."""
     os.makedirs(CACHE, exist_ok=True)
     digest = _sources_digest([os.path.join(CSRC, s) for s in _KERNEL_SRCS])
-    key = hashlib.sha1(("%s|%s|%d|%d|%d" % (header, digest, chunk_nodes, warps,
+    minb = int(os.environ.get("TF_MINB", "2"))
+    key = hashlib.sha1(("%s|%s|%d|%d|%d" % (header, digest, chunk_nodes, minb,
                                             int(fast_div))).encode()).hexdigest()[:20]
     cubin = os.path.join(CACHE, "m_%s.cubin" % key)
     if os.path.exists(cubin):
@@ -85,8 +86,8 @@ def build_cubin(header, chunk_nodes, warps, fast_div=False):
         f.write('#include "tf_kernels.cuh"\n')
     tmp = cubin + ".tmp%d" % os.getpid()
     cmd = [_nvcc(), *ARCH, "-O3", "-std=c++17", "-lineinfo", "-I", CSRC,
-           "-DTF_M=%d" % chunk_nodes, "-DTF_WARPS=%d" % warps,
-           "-DTF_FAST_DIV=%d" % int(fast_div), "-cubin", "-o", tmp, src]
+           "-DTF_M=%d" % chunk_nodes, "-DTF_FAST_DIV=%d" % int(fast_div),
+           "-DTF_MINB=%d" % minb, "-cubin", "-o", tmp, src]
     subprocess.check_call(cmd)
     os.replace(tmp, cubin)
     return cubin

@@ -338,8 +338,8 @@ def _render_header(L, bodies):
     h.append(_switch("tf_j_var", L.j_var))
     h.append(_switch("tf_j_off", L.j_off))
     for which, n in (("F", "TF_NVAR"), ("J", "TF_NNZ")):
-        h.append("TF_HD TF_INLINE void tf_model_%s(const double* TF_RESTRICT cst, "
-                 "const TfNodeIn& in, double (&out)[%s]) {" % (which, n))
+        h.append("template <bool TF_FD> TF_HD TF_INLINE void tf_model_%s(const double* "
+                 "TF_RESTRICT cst, const TfNodeIn& in, double (&out)[%s]) {" % (which, n))
         h.append("  (void)cst; (void)in;")
         h.extend("  " + ln for ln in bodies[which])
         h.append("}")

@@ -143,7 +143,7 @@ class Variant:
 class CompiledModel:
     """Everything the GPU path knows about one ``Model``."""
 
-    def __init__(self, model, fast_div=False, chunk_nodes=None, warps=8, device=None):
+    def __init__(self, model, fast_div=True, chunk_nodes=None, warps=8, device=None):
         self.model = model
         self.fast_div = bool(fast_div)
         self.chunk_nodes = chunk_nodes

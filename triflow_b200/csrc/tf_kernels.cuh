@@ -2,7 +2,7 @@
 //
 // This file is compiled once per model: the generated model header (TF_NVAR,
 // TF_P, ..., tf_model_F, tf_model_J; see triflow_b200/codegen.py) is included
-// first, then this file, with -DTF_M=<nodes per thread> -DTF_WARPS=<warps/CTA>.
+// first, then this file, with -DTF_M=<nodes per thread> (warps per CTA are a launch-time choice).
 //
 // Replaces, on the device (reference file:line):
 //   compute_F_numpy / compute_J_numpy + ghost-cell padding  compilers.py:227-332
@@ -27,12 +27,16 @@
 #ifndef TF_M
 #define TF_M 8
 #endif
-#ifndef TF_WARPS
-#define TF_WARPS 8
+#ifndef TF_FAST_DIV
+#define TF_FAST_DIV 0
+#endif
+#define TF_MAXW 16 /* max warps per CTA (runtime: blockDim.x / 32) */
+#ifndef TF_MINB
+#define TF_MINB 2 /* min CTAs of 512 threads per SM for the sweep kernels (register cap 64) */
 #endif
 
 namespace tfk {
-typedef TfGeom Geom; typedef TfBuf Buf; typedef TfStage Stage; typedef TfUpdate Update;
+typedef TfGeom Geom; typedef TfBuf Buf; typedef TfStage Stage;
 
 constexpr int V = TF_NVAR;
 constexpr int P = TF_P;
@@ -40,8 +44,11 @@ constexpr int BETA = (P * V + V - 1) > 0 ? (P * V + V - 1) : 1;
 constexpr int NB = (P * V) > 0 ? (P * V) : 1;     // border unknowns (last P nodes)
 constexpr int M = TF_M;
 constexpr int C = M * V;
-constexpr int WARPS = TF_WARPS;
-constexpr int NT = 32 * WARPS;
+constexpr int MAXW = TF_MAXW;
+constexpr int NT = 32 * MAXW;         // launch bound of the tile kernels
+constexpr bool FD = TF_FAST_DIV != 0;  // fast division by uniform constants in the solver path
+// the factor kernel keeps whole band rows in registers: fewer threads per CTA for wide bands
+constexpr int NT_FACTOR = (TF_P * TF_NVAR + TF_NVAR - 1) <= 1 ? 512 : 256;
 constexpr int WB = 2 * BETA + 1;
 constexpr int EX = (BETA + V - 1) / V;             // extra nodes needed from the next chunk
 constexpr int NF = TF_NFIELD;
@@ -138,19 +145,44 @@ __device__ __forceinline__ int ld_flag(const int* p) {
   return *((const volatile int*)p);
 }
 
+// "absorbing" maps: composing anything earlier in front of them changes nothing
+// that is used downstream (exact, not approximate: the propagator is exactly 0).
+__device__ __forceinline__ bool absorbing(const Aff& m) {
+  bool z = true;
+#pragma unroll
+  for (int k = 0; k < BETA * BETA; ++k) z = z && (m.d[k] == 0.0);
+  return z;
+}
+__device__ __forceinline__ bool absorbing(const Star& m) {
+  bool zq = true, zs = true;
+#pragma unroll
+  for (int k = 0; k < BETA * BETA; ++k) {
+    zq = zq && (m.Q()[k] == 0.0);
+    zs = zs && (m.S()[k] == 0.0);
+  }
+  return zq || zs;
+}
+
 // Decoupled look-back over the tiles of one system.  Called by all 32 lanes of
 // warp 0 with the tile aggregate; returns the exclusive prefix of the tile.
+// Flags carry the launch epoch (no reset between launches): epoch*4 + {1: aggregate
+// published, 2: inclusive prefix published}.  The walk stops at the nearest
+// inclusive prefix, at the start of the system, or as soon as the accumulated
+// aggregate is absorbing (its propagator underflowed to exactly zero), which for
+// well-conditioned systems happens after a few tiles.
 template <class Mon>
-__device__ Mon lookback(const Mon& aggregate, const Buf& b, long long gbase, int tile, int lane) {
+__device__ Mon lookback(const Mon& aggregate, const Buf& b, long long gbase, int tile, int lane,
+                        int epoch) {
   int* flags = b.flags + 1 + gbase;
   double* agg = b.lbagg + (gbase + tile) * KMAX;
   double* inc = b.lbinc + (gbase + tile) * KMAX;
+  const int FA = epoch * 4 + 1, FI = epoch * 4 + 2;
   if (tile == 0) {
     if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < Mon::K; ++k) inc[k] = aggregate.d[k];
       __threadfence();
-      *((volatile int*)(flags + tile)) = 2;
+      *((volatile int*)(flags + tile)) = FI;
     }
     return Mon::identity();
   }
@@ -158,48 +190,70 @@ __device__ Mon lookback(const Mon& aggregate, const Buf& b, long long gbase, int
 #pragma unroll
     for (int k = 0; k < Mon::K; ++k) agg[k] = aggregate.d[k];
     __threadfence();
-    *((volatile int*)(flags + tile)) = 1;
+    *((volatile int*)(flags + tile)) = FA;
   }
   Mon prefix = Mon::identity();
   int look = tile - 1;
   while (true) {
     const int t = look - lane;            // lane 0 = nearest predecessor
-    int f = 2;
-    if (t >= 0) {
-      do { f = ld_flag(flags + t); } while (f == 0);
-    }
-    __threadfence();
-    const unsigned m2 = __ballot_sync(0xffffffffu, f == 2);
-    const int kstop = __ffs(m2) - 1;      // nearest tile with an inclusive prefix
-    Mon e = Mon::identity();
-    if (t >= 0 && (kstop < 0 || lane <= kstop)) {
-      const double* src = ((f == 2) ? b.lbinc : b.lbagg) + (gbase + t) * KMAX;
+    // wait for the nearest predecessor, then take whatever contiguous run is ready
+    int f = FI;
+    bool conclusive = false;
+    Mon w;
+    for (int attempt = 0; attempt < 2 && !conclusive; ++attempt) {
+      if (t >= 0) {
+        f = ld_flag(flags + t);
+        if (attempt == 0) {
+          if (lane == 0) while (f != FA && f != FI) f = ld_flag(flags + t);
+        } else {
+          while (f != FA && f != FI) f = ld_flag(flags + t);
+        }
+      }
+      __threadfence();
+      const bool ready = (t < 0) || f == FA || f == FI;
+      const unsigned mr = __ballot_sync(0xffffffffu, ready);
+      const unsigned m2 = __ballot_sync(0xffffffffu, ready && (t < 0 || f == FI));
+      const int kr = (~mr == 0u) ? 32 : (__ffs(~mr) - 1);     // contiguous ready lanes
+      const int kstop = __ffs(m2) - 1;                         // nearest inclusive (or start)
+      const int last = (kstop >= 0 && kstop < kr) ? kstop : kr - 1;
+      Mon e = Mon::identity();
+      if (t >= 0 && lane <= last) {
+        const double* src = ((f == FI) ? b.lbinc : b.lbagg) + (gbase + t) * KMAX;
 #pragma unroll
-      for (int k = 0; k < Mon::K; ++k) e.d[k] = __ldcg(src + k);
+        for (int k = 0; k < Mon::K; ++k) e.d[k] = __ldcg(src + k);
+      }
+      w = warp_reduce_rev(e, lane);
+      w = shfl_idx(w, 0);
+      const bool hit = (kstop >= 0 && kstop < kr);
+      const bool absb = absorbing(w);
+      conclusive = hit || absb || kr == 32;
+      if (hit || absb) {
+        prefix = Mon::combine(w, prefix);
+        goto done;
+      }
     }
-    Mon w = warp_reduce_rev(e, lane);
-    w = shfl_idx(w, 0);
-    prefix = Mon::combine(w, prefix);
-    if (kstop >= 0) break;
+    prefix = Mon::combine(w, prefix);     // full window of 32 aggregates, go further back
     look -= 32;
   }
+done:
   if (lane == 0) {
     const Mon incl = Mon::combine(prefix, aggregate);
 #pragma unroll
     for (int k = 0; k < Mon::K; ++k) inc[k] = incl.d[k];
     __threadfence();
-    *((volatile int*)(flags + tile)) = 2;
+    *((volatile int*)(flags + tile)) = FI;
   }
   return prefix;
 }
 
 // Exclusive prefix of every thread's element over (lane, warp, tile) order.
-// `carry` (optional, smem-free) is an extra prefix applied before tile 0 handling
-// when look-back is disabled (used by the border kernel's sequential tile loop).
+// `carry` is the prefix of the tile when look-back is disabled (single tile, or the
+// border kernel's sequential tile loop).
 template <class Mon>
-__device__ Mon tile_scan(const Mon& mine, double* smem /* WARPS*K doubles */, bool use_lookback,
-                         const Buf& b, long long gbase, int tile, const Mon& carry, Mon* tile_total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ Mon tile_scan(const Mon& mine, double* smem /* (MAXW+1)*K doubles */, bool use_lookback,
+                         const Buf& b, long long gbase, int tile, int epoch, const Mon& carry,
+                         Mon* tile_total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const Mon incl = warp_scan(mine, lane);
   Mon excl = shfl_up(incl, 1);
   excl = select(lane == 0, Mon::identity(), excl);
@@ -211,27 +265,26 @@ __device__ Mon tile_scan(const Mon& mine, double* smem /* WARPS*K doubles */, bo
   __syncthreads();
   if (warp == 0) {
     Mon w = Mon::identity();
-    if (lane < WARPS) {
+    if (lane < nwarps) {
 #pragma unroll
       for (int k = 0; k < Mon::K; ++k) w.d[k] = smem[lane * Mon::K + k];
     }
     const Mon wi = warp_scan(w, lane);
     Mon we = shfl_up(wi, 1);
     we = select(lane == 0, Mon::identity(), we);
-    const Mon total = shfl_idx(wi, WARPS - 1);
+    const Mon total = shfl_idx(wi, nwarps - 1);
     Mon tp = carry;
-    if (use_lookback) tp = lookback(total, b, gbase, tile, lane);
+    if (use_lookback) tp = lookback(total, b, gbase, tile, lane, epoch);
     const Mon wp = Mon::combine(tp, we);
     __syncwarp();
-    if (lane < WARPS) {
+    if (lane < nwarps) {
 #pragma unroll
       for (int k = 0; k < Mon::K; ++k) smem[lane * Mon::K + k] = wp.d[k];
     }
     if (tile_total != nullptr && lane == 0) {
-      // inclusive total of the tile including carry, parked after the warp slots
       const Mon tt = Mon::combine(tp, total);
 #pragma unroll
-      for (int k = 0; k < Mon::K; ++k) smem[WARPS * Mon::K + k] = tt.d[k];
+      for (int k = 0; k < Mon::K; ++k) smem[MAXW * Mon::K + k] = tt.d[k];
     }
   }
   __syncthreads();
@@ -240,23 +293,24 @@ __device__ Mon tile_scan(const Mon& mine, double* smem /* WARPS*K doubles */, bo
   for (int k = 0; k < Mon::K; ++k) wp.d[k] = smem[warp * Mon::K + k];
   if (tile_total != nullptr) {
 #pragma unroll
-    for (int k = 0; k < Mon::K; ++k) tile_total->d[k] = smem[WARPS * Mon::K + k];
+    for (int k = 0; k < Mon::K; ++k) tile_total->d[k] = smem[MAXW * Mon::K + k];
   }
   return Mon::combine(wp, excl);
 }
 
-// Tile / system assignment.  One tile per system: blockIdx.  Otherwise a ticket,
-// so that every tile a CTA may wait for is already running (look-back progress).
+// Tile / system assignment.  One tile per system: blockIdx.  Otherwise a ticket
+// (monotone counter, the launch's base is passed in), so that every tile a CTA
+// may wait for is already running (look-back forward progress).
 __device__ __forceinline__ void resolve_tile(const Geom& g, const Buf& b, int& sys, int& tile) {
   if (g.tiles == 1) {
     sys = blockIdx.x;
     tile = 0;
     return;
   }
-  __shared__ int s_ticket;
-  if (threadIdx.x == 0) s_ticket = atomicAdd(b.flags, 1);
+  __shared__ unsigned s_ticket;
+  if (threadIdx.x == 0) s_ticket = atomicAdd((unsigned*)b.flags, 1u) - (unsigned)g.ticket_base;
   __syncthreads();
-  const int t = s_ticket;
+  const int t = (int)s_ticket;
   sys = t / g.tiles;
   tile = t - sys * g.tiles;
 }
@@ -264,29 +318,57 @@ __device__ __forceinline__ void resolve_tile(const Geom& g, const Buf& b, int& s
 // ------------------------------------------------------------ stencil windows
 // Values of every field at nodes i0-P .. i0+NODES-1+P for the stage state
 // U + sum_j alpha_j K_j (dependent variables) and the helper planes.
-template <int NODES>
+// stage state of one unknown: U + ((alpha_0 k_0 + alpha_1 k_1) + ...) in the reference's
+// summation order (schemes.py:153-155).  NPREV < 0: number of terms known at run time.
+template <int NPREV>
+__device__ __forceinline__ double stage_value(const double* __restrict__ U, const Buf& b,
+                                              long long sysoff, long long a, const Stage* st) {
+  double u = U[a];
+  constexpr int NQ = NPREV < 0 ? MAXS : NPREV;
+  if (NQ > 0 && st != nullptr) {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      if (NPREV >= 0 || q < st->nprev) {
+        const double term = __dmul_rn(st->alpha[q], b.K[q][sysoff + a]);
+        acc = (q == 0) ? term : __dadd_rn(acc, term);
+      }
+    if (NPREV >= 0 || st->nprev > 0) u = __dadd_rn(u, acc);
+  }
+  return u;
+}
+
+template <int NODES, int NPREV>
 __device__ __forceinline__ void load_windows(double (&win)[NF][NODES + 2 * P], int i0, const Geom& g,
                                              const Buf& b, int sys, const Stage* st) {
-  const double* U = b.U + sys * vstride(g);
+  const long long so = sys * vstride(g);
+  const double* U = b.U + so;
+  const int chunk = i0 / M;
+  if (i0 >= P && i0 + NODES + P <= g.N && NODES + P <= 2 * M && P <= M) {
+    // interior: every window node is a real node of this, the previous or the next
+    // chunk(s): addresses are lane-neighbours of the own chunk, offsets are constants
+#pragma unroll
+    for (int w = 0; w < NODES + 2 * P; ++w) {
+      const int rel = w - P;                               // node offset from i0
+      const int dc = rel < 0 ? -1 : (rel >= M ? 1 : 0);    // neighbour chunk (compile time)
+      const int m = rel - dc * M;
+      const int ch = chunk + dc;
+      const long long cb = ((long long)(ch >> 5) * C) * 32 + (ch & 31);
+      const long long hb = ((long long)(ch >> 5) * M) * 32 + (ch & 31);
+#pragma unroll
+      for (int e = 0; e < V; ++e)
+        win[e][w] = stage_value<NPREV>(U, b, so, cb + (long long)(m * V + e) * 32, st);
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+        win[V + h][w] = b.H[(sys * (long long)NH + h) * hstride(g) + hb + (long long)m * 32];
+    }
+    return;
+  }
 #pragma unroll
   for (int w = 0; w < NODES + 2 * P; ++w) {
     const int j = map_node(i0 - P + w, g);
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const long long a = vidx(j, e);
-      double u = U[a];
-      if (st != nullptr && st->nprev > 0) {
-        double acc = 0.0;
-#pragma unroll
-        for (int q = 0; q < MAXS; ++q)
-          if (q < st->nprev) {
-            const double term = __dmul_rn(st->alpha[q], b.K[q][sys * vstride(g) + a]);
-            acc = (q == 0) ? term : __dadd_rn(acc, term);
-          }
-        u = __dadd_rn(u, acc);
-      }
-      win[e][w] = u;
-    }
+    for (int e = 0; e < V; ++e) win[e][w] = stage_value<NPREV>(U, b, so, vidx(j, e), st);
 #pragma unroll
     for (int h = 0; h < NH; ++h)
       win[V + h][w] = b.H[(sys * (long long)NH + h) * hstride(g) + nidx(j)];
@@ -368,7 +450,7 @@ __device__ __forceinline__ void assemble_rows(double (&A)[C + BETA][WB], int i0,
                                               const Buf& b, int sys, double a, const double* cst) {
   constexpr int NODES = M + EX;
   double win[NF][NODES + 2 * P];
-  load_windows<NODES>(win, i0, g, b, sys, nullptr);
+  load_windows<NODES, 0>(win, i0, g, b, sys, nullptr);
   const int npad = g.nblk * 32 * M;
 #pragma unroll
   for (int m = 0; m < NODES; ++m) {
@@ -383,7 +465,7 @@ __device__ __forceinline__ void assemble_rows(double (&A)[C + BETA][WB], int i0,
       if (i < g.N) {
         TfNodeIn in;
         node_inputs<NODES>(in, win, m, i, g, b, sys);
-        tf_model_J(cst, in, jv);
+        tf_model_J<FD>(cst, in, jv);
       }
       if (i >= P && i < g.N - 2 * P) {
 #pragma unroll
@@ -451,16 +533,16 @@ extern "C" __global__ void tf_k_unpack(Geom g, const double* __restrict__ src, d
 }
 
 // F(U) in natural layout (compatibility path of model.F), one thread per chunk
-extern "C" __global__ void __launch_bounds__(NT) tf_k_eval_F(Geom g, Buf b, double* __restrict__ out) {
+extern "C" __global__ void __launch_bounds__(256) tf_k_eval_F(Geom g, Buf b, double* __restrict__ out) {
   const int chunks = g.nblk * 32;
-  const long long t = blockIdx.x * (long long)NT + threadIdx.x;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)chunks * g.batch) return;
   const int sys = (int)(t / chunks), chunk = (int)(t % chunks);
   const int i0 = chunk * M;
   if (i0 >= g.N) return;
   const double* cst = b.cst + (long long)sys * NC2;
   double win[NF][M + 2 * P];
-  load_windows<M>(win, i0, g, b, sys, nullptr);
+  load_windows<M, 0>(win, i0, g, b, sys, nullptr);
 #pragma unroll
   for (int m = 0; m < M; ++m) {
     const int i = i0 + m;
@@ -468,7 +550,7 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_eval_F(Geom g, Buf b, doub
       TfNodeIn in;
       node_inputs<M>(in, win, m, i, g, b, sys);
       double f[V];
-      tf_model_F(cst, in, f);
+      tf_model_F<false>(cst, in, f);
 #pragma unroll
       for (int e = 0; e < V; ++e) out[((long long)sys * g.N + i) * V + e] = f[e];
     }
@@ -476,16 +558,16 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_eval_F(Geom g, Buf b, doub
 }
 
 // nonzero Jacobian values per node, natural layout [sys][node][nnz]
-extern "C" __global__ void __launch_bounds__(NT) tf_k_eval_J(Geom g, Buf b, double* __restrict__ out) {
+extern "C" __global__ void __launch_bounds__(256) tf_k_eval_J(Geom g, Buf b, double* __restrict__ out) {
   const int chunks = g.nblk * 32;
-  const long long t = blockIdx.x * (long long)NT + threadIdx.x;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)chunks * g.batch) return;
   const int sys = (int)(t / chunks), chunk = (int)(t % chunks);
   const int i0 = chunk * M;
   if (i0 >= g.N) return;
   const double* cst = b.cst + (long long)sys * NC2;
   double win[NF][M + 2 * P];
-  load_windows<M>(win, i0, g, b, sys, nullptr);
+  load_windows<M, 0>(win, i0, g, b, sys, nullptr);
 #pragma unroll
   for (int m = 0; m < M; ++m) {
     const int i = i0 + m;
@@ -493,7 +575,7 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_eval_J(Geom g, Buf b, doub
       TfNodeIn in;
       node_inputs<M>(in, win, m, i, g, b, sys);
       double jv[NNZ];
-      tf_model_J(cst, in, jv);
+      tf_model_J<false>(cst, in, jv);
 #pragma unroll
       for (int k = 0; k < NNZ; ++k) out[((long long)sys * g.N + i) * NNZ + k] = jv[k];
     }
@@ -501,15 +583,16 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_eval_J(Geom g, Buf b, doub
 }
 
 // ---- factor: A = I - a*J(U) -> banded LU (chunk scan with linear-fractional maps)
-extern "C" __global__ void __launch_bounds__(NT) tf_k_factor(Geom g, Buf b, double a) {
-  __shared__ double smem[(WARPS + 1) * KMAX];
+extern "C" __global__ void __launch_bounds__(NT_FACTOR) tf_k_factor(Geom g, Buf b, double a) {
+  __shared__ double smem[(MAXW + 1) * KMAX];
   int sys, tile;
   resolve_tile(g, b, sys, tile);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int blk = tile * WARPS + warp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int blk = tile * nwarps + warp;
   const bool active = blk < g.nblk;
   const int chunk = blk * 32 + lane;
   const double* cst = b.cst + (long long)sys * NC2;
+  if (tile == 0 && threadIdx.x == 0) b.err[sys] = 0.0;     // consumed by the last bwd
   double A[C + BETA][WB];
   Star mine = Star::identity();
   int bad = 0;
@@ -518,7 +601,7 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_factor(Geom g, Buf b, doub
     tfb::ChunkLU<BETA, C>::run1(A, mine, bad);
   }
   const Star pre = tile_scan<Star>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
-                                   Star::identity(), nullptr);
+                                   g.epoch, Star::identity(), nullptr);
   if (active) {
     double Uf[C][BETA + 1], Lown[C][BETA], Lnext[BETA][BETA];
     tfb::ChunkLU<BETA, C>::run2(A, pre.P(), Uf, Lown, Lnext, bad);
@@ -527,7 +610,8 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_factor(Geom g, Buf b, doub
 #pragma unroll
     for (int r = 0; r < C; ++r) {
 #pragma unroll
-      for (int q = 0; q <= BETA; ++q) Ug[((long long)blk * C + r) * 32 * (BETA + 1) + q * 32 + lane] = Uf[r][q];
+      for (int q = 0; q <= BETA; ++q)
+        Ug[((long long)blk * C + r) * 32 * (BETA + 1) + q * 32 + lane] = Uf[r][q];
 #pragma unroll
       for (int q = 1; q <= BETA; ++q)
         if (q <= r) Lg[((long long)blk * C + r) * 32 * BETA + (q - 1) * 32 + lane] = Lown[r][q - 1];
@@ -546,66 +630,6 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_factor(Geom g, Buf b, doub
   }
 }
 
-// ---- forward substitution of one stage: rhs = dt*F(U_i) + sum cfac_j k_j ; L y = rhs
-extern "C" __global__ void __launch_bounds__(NT) tf_k_fwd(Geom g, Buf b, Stage st) {
-  __shared__ double smem[(WARPS + 1) * KMAX];
-  int sys, tile;
-  resolve_tile(g, b, sys, tile);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int blk = tile * WARPS + warp;
-  const bool active = blk < g.nblk;
-  const int chunk = blk * 32 + lane;
-  const int i0 = chunk * M;
-  const double* cst = b.cst + (long long)sys * NC2;
-  const long long vs = vstride(g);
-  double L[C][BETA], f[C], y[C];
-  Aff mine = Aff::identity();
-  if (active) {
-    double win[NF][M + 2 * P];
-    load_windows<M>(win, i0, g, b, sys, &st);
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-      const int i = i0 + m;
-      double fe[V];
-#pragma unroll
-      for (int e = 0; e < V; ++e) fe[e] = 0.0;
-      if (i < g.N) {
-        TfNodeIn in;
-        node_inputs<M>(in, win, m, i, g, b, sys);
-        tf_model_F(cst, in, fe);
-      }
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        const int r = m * V + e;
-        double rhs = st.dt * fe[e];
-        const long long a = ((long long)blk * C + r) * 32 + lane;
-#pragma unroll
-        for (int q = 0; q < MAXS; ++q)
-          if (q < st.nprev) rhs += st.cfac[q] * b.K[q][sys * vs + a];
-        f[r] = (i < g.N) ? rhs : 0.0;
-      }
-    }
-    const double* Lg = b.Lf + sys * vs * BETA;
-#pragma unroll
-    for (int r = 0; r < C; ++r)
-#pragma unroll
-      for (int q = 0; q < BETA; ++q) L[r][q] = Lg[((long long)blk * C + r) * 32 * BETA + q * 32 + lane];
-    double s0[BETA];
-#pragma unroll
-    for (int t = 0; t < BETA; ++t) s0[t] = 0.0;
-    tfb::fwd_chunk<BETA, C>(L, f, s0, y);
-    tfb::fwd_map<BETA, C>(L, y, mine);
-  }
-  const Aff pre = tile_scan<Aff>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
-                                 Aff::identity(), nullptr);
-  if (active) {
-    tfb::fwd_chunk<BETA, C>(L, f, pre.c(), y);
-    double* Y = b.Y + sys * vs;
-#pragma unroll
-    for (int r = 0; r < C; ++r) Y[((long long)blk * C + r) * 32 + lane] = y[r];
-  }
-}
-
 // ---- border fill.  The last P nodes ("border", NB unknowns) are ordered last:
 //   [ A^  E ] = [ L^   0 ] [ U^  W ]      W = L^-1 E   (fill column, NB per row)
 //   [ F^T Ab]   [ G^T  I ] [ 0   S ]      G^T = F^T U^-1 (fill row),  S = Ab - G^T W
@@ -620,113 +644,135 @@ __device__ __forceinline__ long long fidx(int R, int q, int width) {
 }
 
 extern "C" __global__ void __launch_bounds__(NT) tf_k_border_fill(Geom g, Buf b, double a) {
-  __shared__ double smem[(WARPS + 1) * KMAX];
-  __shared__ double s_red[WARPS][NB * NB];
+  __shared__ double smem[(MAXW + 1) * KMAX];
+  __shared__ double s_red[MAXW][NB * NB];
   __shared__ int s_alive;
   const int sys = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const long long vs = vstride(g);
   const double* bt = b.btab + (long long)sys * 5 * NB * NB;
   const double* Lg = b.Lf + sys * vs * BETA;
   const double* Ug = b.Uf + sys * vs * (BETA + 1);
   double* Wg = b.Wb + sys * vs * NB;
   double* Gg = b.Gb + sys * vs * NB;
-  const int ntile = (g.nblk + WARPS - 1) / WARPS;
-  const int tile_rows = WARPS * 32 * C;
+  const int ntile = (g.nblk + nwarps - 1) / nwarps;
+  const int tile_rows = nwarps * 32 * C;
   const int bot0 = g.nhat - NB;
-  const int tail0 = bot0 / tile_rows;
-  double cw[NB][BETA], cg[NB][BETA];            // carried recurrence states
-#pragma unroll
-  for (int c = 0; c < NB; ++c)
-#pragma unroll
-    for (int t = 0; t < BETA; ++t) { cw[c][t] = 0.0; cg[c][t] = 0.0; }
-  int lead_rows = -1;
-  int tile = 0;
-  while (tile < ntile) {
-    const int blk = tile * WARPS + warp;
-    const bool active = blk < g.nblk;
-    const int chunk = blk * 32 + lane;
-    const int r0 = chunk * C;
-    double L[C][BETA], L2[C][BETA], inv[C];
-    if (active) {
-#pragma unroll
-      for (int r = 0; r < C; ++r) {
-#pragma unroll
-        for (int q = 0; q < BETA; ++q) L[r][q] = Lg[((long long)blk * C + r) * 32 * BETA + q * 32 + lane];
-        inv[r] = Ug[((long long)blk * C + r) * 32 * (BETA + 1) + lane];
-#pragma unroll
-        for (int q = 1; q <= BETA; ++q) {
-          const int R = r0 + r - q;
-          L2[r][q - 1] = (R >= 0) ? Ug[fidx(R, q, BETA + 1)] * Ug[fidx(R, 0, BETA + 1)] : 0.0;
-        }
-      }
-    }
-#pragma unroll 1
-    for (int pass = 0; pass < 2 * NB; ++pass) {
-      const bool isW = pass < NB;
-      const int c = isW ? pass : pass - NB;
-      double f[C], y[C];
-      Aff mine = Aff::identity();
-      if (active) {
-#pragma unroll
-        for (int r = 0; r < C; ++r) {
-          const int gr = r0 + r;
-          double v = 0.0;
-          if (gr < NB) v = isW ? bt[0 * NB * NB + gr * NB + c] : bt[2 * NB * NB + c * NB + gr];
-          else if (gr >= bot0 && gr < g.nhat)
-            v = isW ? bt[1 * NB * NB + (gr - bot0) * NB + c] : bt[3 * NB * NB + c * NB + (gr - bot0)];
-          f[r] = -(a * v);
-        }
-        double s0[BETA];
-#pragma unroll
-        for (int t = 0; t < BETA; ++t) s0[t] = 0.0;
-        if (isW) { tfb::fwd_chunk<BETA, C>(L, f, s0, y); tfb::fwd_map<BETA, C>(L, y, mine); }
-        else { tfb::fwd_chunk<BETA, C>(L2, f, s0, y); tfb::fwd_map<BETA, C>(L2, y, mine); }
-      }
-      Aff carry;
-#pragma unroll
-      for (int k = 0; k < BETA * BETA; ++k) carry.d[k] = 0.0;
-#pragma unroll
-      for (int t = 0; t < BETA; ++t) {
-        double v = 0.0;
-#pragma unroll
-        for (int cc = 0; cc < NB; ++cc) if (cc == c) v = isW ? cw[cc][t] : cg[cc][t];
-        carry.c()[t] = v;
-      }
-      Aff total;
-      const Aff pre = tile_scan<Aff>(mine, smem, false, b, 0, 0, carry, &total);
-#pragma unroll
-      for (int t = 0; t < BETA; ++t)
-#pragma unroll
-        for (int cc = 0; cc < NB; ++cc) if (cc == c) { if (isW) cw[cc][t] = total.c()[t]; else cg[cc][t] = total.c()[t]; }
-      if (active) {
-        if (isW) tfb::fwd_chunk<BETA, C>(L, f, pre.c(), y);
-        else tfb::fwd_chunk<BETA, C>(L2, f, pre.c(), y);
-#pragma unroll
-        for (int r = 0; r < C; ++r) {
-          const long long o = ((long long)blk * C + r) * 32 * NB + c * 32 + lane;
-          if (isW) Wg[o] = y[r]; else Gg[o] = y[r] * inv[r];
-        }
-      }
-    }
-    // continue while any carried state is non-zero
-    bool alive = false;
+  // ---- top part: periodic corner entries (E_top, F_top).  Skipped when they vanish
+  //      (non-periodic systems), otherwise walk tiles until the carried state is 0.
+  bool any_top = false;
+  for (int k = 0; k < NB * NB; ++k)
+    any_top = any_top || (bt[0 * NB * NB + k] != 0.0) || (bt[2 * NB * NB + k] != 0.0);
+  int lead_rows = 0;
+  if (any_top) {
+    double cw[NB][BETA], cg[NB][BETA];            // carried recurrence states
 #pragma unroll
     for (int c = 0; c < NB; ++c)
 #pragma unroll
-      for (int t = 0; t < BETA; ++t) alive = alive || (cw[c][t] != 0.0) || (cg[c][t] != 0.0);
-    __syncthreads();
-    if (threadIdx.x == 0) s_alive = alive ? 1 : 0;
-    __syncthreads();
-    alive = s_alive != 0;
-    int rows_done = (tile + 1) * tile_rows;
-    if (rows_done > g.nhat) rows_done = g.nhat;
-    if (lead_rows < 0) {
-      if (!alive || tile + 1 >= ntile) { lead_rows = rows_done; }
+      for (int t = 0; t < BETA; ++t) { cw[c][t] = 0.0; cg[c][t] = 0.0; }
+    for (int tile = 0; tile < ntile; ++tile) {
+      const int blk = tile * nwarps + warp;
+      const bool active = blk < g.nblk;
+      const int chunk = blk * 32 + lane;
+      const int r0 = chunk * C;
+      double L[C][BETA], L2[C][BETA], inv[C];
+      if (active) {
+#pragma unroll
+        for (int r = 0; r < C; ++r) {
+#pragma unroll
+          for (int q = 0; q < BETA; ++q) L[r][q] = Lg[((long long)blk * C + r) * 32 * BETA + q * 32 + lane];
+          inv[r] = Ug[((long long)blk * C + r) * 32 * (BETA + 1) + lane];
+#pragma unroll
+          for (int q = 1; q <= BETA; ++q) {
+            const int R = r0 + r - q;
+            L2[r][q - 1] = (R >= 0) ? Ug[fidx(R, q, BETA + 1)] * Ug[fidx(R, 0, BETA + 1)] : 0.0;
+          }
+        }
+      }
+#pragma unroll 1
+      for (int pass = 0; pass < 2 * NB; ++pass) {
+        const bool isW = pass < NB;
+        const int c = isW ? pass : pass - NB;
+        double f[C], y[C];
+        Aff mine = Aff::identity();
+        if (active) {
+#pragma unroll
+          for (int r = 0; r < C; ++r) {
+            const int gr = r0 + r;
+            double v = 0.0;
+            if (gr < NB) v = isW ? bt[0 * NB * NB + gr * NB + c] : bt[2 * NB * NB + c * NB + gr];
+            f[r] = -(a * v);
+          }
+          double s0[BETA];
+#pragma unroll
+          for (int t = 0; t < BETA; ++t) s0[t] = 0.0;
+          if (isW) { tfb::fwd_chunk<BETA, C>(L, f, s0, y); tfb::fwd_map<BETA, C>(L, y, mine); }
+          else { tfb::fwd_chunk<BETA, C>(L2, f, s0, y); tfb::fwd_map<BETA, C>(L2, y, mine); }
+        }
+        Aff carry;
+#pragma unroll
+        for (int k = 0; k < BETA * BETA; ++k) carry.d[k] = 0.0;
+#pragma unroll
+        for (int t = 0; t < BETA; ++t) {
+          double v = 0.0;
+#pragma unroll
+          for (int cc = 0; cc < NB; ++cc) if (cc == c) v = isW ? cw[cc][t] : cg[cc][t];
+          carry.c()[t] = v;
+        }
+        Aff total;
+        const Aff pre = tile_scan<Aff>(mine, smem, false, b, 0, 0, 0, carry, &total);
+#pragma unroll
+        for (int t = 0; t < BETA; ++t)
+#pragma unroll
+          for (int cc = 0; cc < NB; ++cc)
+            if (cc == c) { if (isW) cw[cc][t] = total.c()[t]; else cg[cc][t] = total.c()[t]; }
+        if (active) {
+          if (isW) tfb::fwd_chunk<BETA, C>(L, f, pre.c(), y);
+          else tfb::fwd_chunk<BETA, C>(L2, f, pre.c(), y);
+#pragma unroll
+          for (int r = 0; r < C; ++r) {
+            const long long o = ((long long)blk * C + r) * 32 * NB + c * 32 + lane;
+            if (isW) Wg[o] = y[r]; else Gg[o] = y[r] * inv[r];
+          }
+        }
+      }
+      bool alive = false;
+#pragma unroll
+      for (int c = 0; c < NB; ++c)
+#pragma unroll
+        for (int t = 0; t < BETA; ++t) alive = alive || (cw[c][t] != 0.0) || (cg[c][t] != 0.0);
+      __syncthreads();
+      if (threadIdx.x == 0) s_alive = alive ? 1 : 0;
+      __syncthreads();
+      lead_rows = (tile + 1) * tile_rows;
+      if (lead_rows > g.nhat) lead_rows = g.nhat;
+      if (s_alive == 0) break;
     }
-    if (lead_rows >= 0 && tile + 1 < tail0 && !alive) tile = tail0; else tile = tile + 1;
   }
-  if (lead_rows < 0) lead_rows = g.nhat;
+  __syncthreads();
+  // ---- bottom part: the natural coupling of the last NB interior rows to the border
+  //      (E_bot, F_bot).  L^-1 only propagates downwards, so it is a local NB-row solve,
+  //      superposed on what the top part left in those rows.
+  if (threadIdx.x < 2 * NB) {
+    const bool isW = threadIdx.x < NB;
+    const int c = isW ? threadIdx.x : threadIdx.x - NB;
+    double loc[NB];
+    for (int j = 0; j < NB; ++j) {
+      const int gr = bot0 + j;
+      double v = -(a * (isW ? bt[1 * NB * NB + j * NB + c] : bt[3 * NB * NB + c * NB + j]));
+      for (int q = 1; q <= BETA; ++q) {
+        const int jj = j - q;
+        if (jj < 0) break;
+        const double coef = isW ? Lg[fidx(gr, q - 1, BETA)]
+                                : Ug[fidx(gr - q, q, BETA + 1)] * Ug[fidx(gr - q, 0, BETA + 1)];
+        v -= coef * loc[jj];
+      }
+      loc[j] = v;
+      const double out = isW ? v : v * Ug[fidx(gr, 0, BETA + 1)];
+      double* dst = (isW ? Wg : Gg) + fidx(gr, c, NB);
+      *dst = (gr < lead_rows ? *dst : 0.0) + out;
+    }
+  }
   __syncthreads();
   // S = (I - a Ab) - sum_r G[r][.]^T W[r][.] over rows where both may be non-zero
   double part[NB][NB];
@@ -738,7 +784,7 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_border_fill(Geom g, Buf b,
   for (int pass = 0; pass < 2; ++pass) {
     const int lo = pass == 0 ? 0 : (lead_rows > bot0 ? lead_rows : bot0);
     const int hi = pass == 0 ? lead_rows : g.nhat;
-    for (int r = lo + threadIdx.x; r < hi; r += NT) {
+    for (int r = lo + threadIdx.x; r < hi; r += blockDim.x) {
       double gv[NB], wv[NB];
 #pragma unroll
       for (int c = 0; c < NB; ++c) { gv[c] = Gg[fidx(r, c, NB)]; wv[c] = Wg[fidx(r, c, NB)]; }
@@ -763,7 +809,7 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_border_fill(Geom g, Buf b,
     for (int i = 0; i < NB; ++i)
       for (int j = 0; j < NB; ++j) {
         double v = 0.0;
-        for (int w = 0; w < WARPS; ++w) v += s_red[w][i * NB + j];
+        for (int w = 0; w < nwarps; ++w) v += s_red[w][i * NB + j];
         S[i * NB + j] = ((i == j) ? 1.0 : 0.0) - a * bt[4 * NB * NB + i * NB + j] - v;
         I[i * NB + j] = (i == j) ? 1.0 : 0.0;
       }
@@ -779,156 +825,325 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_border_fill(Geom g, Buf b,
   }
 }
 
-// ---- border solve: x_b = S^-1 (y_b - G^T y)   (one warp per system)
-extern "C" __global__ void tf_k_border_solve(Geom g, Buf b) {
-  const int sys = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (sys >= g.batch) return;
+// rows of the border fill that may be non-zero: the leading `lead` rows and the last
+// NB interior rows
+__device__ __forceinline__ bool fill_row(int gr, int lead, const Geom& g) {
+  return gr < lead || (gr >= g.nhat - NB && gr < g.nhat);
+}
+
+// ---- forward substitution of one stage: rhs = dt*F(U_i) + sum cfac_j k_j ; L y = rhs
+//      + per-tile partial sums of G^T y for the border solve
+// Streaming recurrences: only the last BETA values of the solution and of the BETA
+// homogeneous solutions are kept, so the register footprint is O(BETA^2) and the
+// factor rows are consumed as they arrive; the second pass re-reads them (L1/L2 hits).
+struct RecState {
+  double s[BETA];          // s[t] = value at distance t+1 behind the current row
+  double h[BETA][BETA];    // h[j][t]: same for the homogeneous solution started from e_j
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int t = 0; t < BETA; ++t) {
+      s[t] = 0.0;
+#pragma unroll
+      for (int j = 0; j < BETA; ++j) h[j][t] = (j == t) ? 1.0 : 0.0;
+    }
+  }
+  // coef[q-1] multiplies the value q rows behind; scale multiplies the result
+  __device__ __forceinline__ void step(const double (&coef)[BETA], double rhs, double scale) {
+    double v = rhs;
+#pragma unroll
+    for (int q = 0; q < BETA; ++q) v -= coef[q] * s[q];
+    v *= scale;
+#pragma unroll
+    for (int q = BETA - 1; q > 0; --q) s[q] = s[q - 1];
+    s[0] = v;
+#pragma unroll
+    for (int j = 0; j < BETA; ++j) {
+      double w = 0.0;
+#pragma unroll
+      for (int q = 0; q < BETA; ++q) w -= coef[q] * h[j][q];
+      w *= scale;
+#pragma unroll
+      for (int q = BETA - 1; q > 0; --q) h[j][q] = h[j][q - 1];
+      h[j][0] = w;
+    }
+  }
+  __device__ __forceinline__ void to_map(Aff& m) const {
+#pragma unroll
+    for (int i = 0; i < BETA; ++i) {
+      m.c()[i] = s[i];
+#pragma unroll
+      for (int j = 0; j < BETA; ++j) m.Phi()[i * BETA + j] = h[j][i];
+    }
+  }
+};
+
+template <int NPREV>
+__device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stage& st) {
+  __shared__ double smem[(MAXW + 1) * KMAX];
+  __shared__ double s_part[MAXW][NB];
+  extern __shared__ double s_f[];                 // [C][blockDim.x] right-hand side stash
+  int sys, tile;
+  resolve_tile(g, b, sys, tile);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int blk = tile * nwarps + warp;
+  const bool active = blk < g.nblk;
+  const int chunk = blk * 32 + lane;
+  const int i0 = chunk * M;
+  const double* cst = b.cst + (long long)sys * NC2;
   const long long vs = vstride(g);
-  const double* Y = b.Y + sys * vs;
-  const double* G = b.Gb + sys * vs * NB;
+  const long long cb = ((long long)blk * C) * 32 + lane;          // own chunk, element 0
+  const double* Lg = b.Lf + sys * vs * BETA + cb * BETA - (long long)lane * (BETA - 1);
+  Aff mine = Aff::identity();
+  if (active) {
+    double win[NF][M + 2 * P];
+    load_windows<M, NPREV>(win, i0, g, b, sys, &st);
+    RecState rs;
+    rs.init();
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      const int i = i0 + m;
+      double fe[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) fe[e] = 0.0;
+      if (i < g.N) {
+        TfNodeIn in;
+        node_inputs<M>(in, win, m, i, g, b, sys);
+        tf_model_F<FD>(cst, in, fe);
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const int r = m * V + e;
+        double rhs = st.dt * fe[e];
+#pragma unroll
+        for (int q = 0; q < (NPREV < 0 ? MAXS : NPREV); ++q)
+          if (NPREV >= 0 || q < st.nprev) rhs += st.cfac[q] * b.K[q][sys * vs + cb + (long long)r * 32];
+        rhs = (i < g.N) ? rhs : 0.0;
+        s_f[r * blockDim.x + threadIdx.x] = rhs;
+        double coef[BETA];
+#pragma unroll
+        for (int q = 0; q < BETA; ++q) coef[q] = Lg[((long long)r * BETA + q) * 32];
+        rs.step(coef, rhs, 1.0);
+      }
+    }
+    rs.to_map(mine);
+  }
+  const Aff pre = tile_scan<Aff>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
+                                 g.epoch, Aff::identity(), nullptr);
+  // second pass with the true incoming state; partial G^T y of the tile on the fly
+  const int tile_rows = nwarps * 32 * C;
   const int glead = b.lead[sys * 2 + 1];
+  const int t0 = tile * tile_rows, t1 = t0 + tile_rows;
+  const bool gtile = t0 < glead || (t1 > g.nhat - NB && t0 < g.nhat);
   double acc[NB];
 #pragma unroll
   for (int c = 0; c < NB; ++c) acc[c] = 0.0;
-  const int bot0 = g.nhat - NB;
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const int lo = pass == 0 ? 0 : (glead > bot0 ? glead : bot0);
-    const int hi = pass == 0 ? (glead < g.nhat ? glead : g.nhat) : g.nhat;
-    for (int r = lo + lane; r < hi; r += 32) {
-      const long long a = ridx(r);
-      const double yr = Y[a];
+  if (active) {
+    double sv[BETA];
 #pragma unroll
-      for (int c = 0; c < NB; ++c) acc[c] += G[(a >> 5) * 32 * NB + c * 32 + (a & 31)] * yr;
+    for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
+    double* Y = b.Y + sys * vs + cb;
+    const double* G = b.Gb + sys * vs * NB + cb * NB - (long long)lane * (NB - 1);
+    const int r0 = chunk * C;
+#pragma unroll
+    for (int r = 0; r < C; ++r) {
+      double v = s_f[r * blockDim.x + threadIdx.x];
+#pragma unroll
+      for (int q = 0; q < BETA; ++q) v -= Lg[((long long)r * BETA + q) * 32] * sv[q];
+#pragma unroll
+      for (int q = BETA - 1; q > 0; --q) sv[q] = sv[q - 1];
+      sv[0] = v;
+      Y[(long long)r * 32] = v;
+      if (gtile && fill_row(r0 + r, glead, g)) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) acc[c] += G[((long long)r * NB + c) * 32] * v;
+      }
     }
   }
+  if (gtile) {
 #pragma unroll
-  for (int c = 0; c < NB; ++c)
+    for (int c = 0; c < NB; ++c) {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], d);
-  if (lane == 0) {
-    double yb[NB];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) yb[c] = Y[ridx(g.nhat + c)] - acc[c];
-    const double* Si = b.Sinv + (long long)sys * NB * NB;
-#pragma unroll
-    for (int r = 0; r < NB; ++r) {
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < NB; ++c) s += Si[r * NB + c] * yb[c];
-      b.xb[(long long)sys * NB + r] = s;
+      for (int d = 16; d > 0; d >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], d);
+      if (lane == 0) s_part[warp][c] = acc[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < NB) {
+      double v = 0.0;
+      for (int w = 0; w < nwarps; ++w) v += s_part[w][threadIdx.x];
+      b.gpart[((long long)sys * g.tiles + tile) * NB + threadIdx.x] = v;
     }
   }
 }
 
-// ---- backward substitution: U x = y - W x_b ; k_i = x - sum cfac_j k_j
-extern "C" __global__ void __launch_bounds__(NT) tf_k_bwd(Geom g, Buf b, Stage st) {
-  __shared__ double smem[(WARPS + 1) * KMAX];
+#define TF_FWD_KERNEL(name, NP)                                                          \
+  extern "C" __global__ void __launch_bounds__(NT, TF_MINB) name(Geom g, Buf b, Stage st) { \
+    fwd_body<NP>(g, b, st);                                                               \
+  }
+TF_FWD_KERNEL(tf_k_fwd0, 0)
+TF_FWD_KERNEL(tf_k_fwd1, 1)
+TF_FWD_KERNEL(tf_k_fwd2, 2)
+TF_FWD_KERNEL(tf_k_fwdg, -1)
+
+// x_b = S^-1 (y_b - sum of the fwd tiles' partial G^T y), fixed summation order
+__device__ __forceinline__ void border_solution(double (&xb)[NB], const Geom& g, const Buf& b,
+                                                int sys, int fwd_tiles, int fwd_tile_rows) {
+  const double* Y = b.Y + sys * vstride(g);
+  const int glead = b.lead[sys * 2 + 1];
+  double acc[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) acc[c] = 0.0;
+  const int nlead = (glead + fwd_tile_rows - 1) / fwd_tile_rows;
+  const int tail0 = (g.nhat - NB) / fwd_tile_rows, tail1 = (g.nhat - 1) / fwd_tile_rows;
+  for (int t = 0; t < fwd_tiles; ++t) {
+    if (t < nlead || (t >= tail0 && t <= tail1)) {
+#pragma unroll
+      for (int c = 0; c < NB; ++c) acc[c] += __ldcg(b.gpart + ((long long)sys * fwd_tiles + t) * NB + c);
+    } else if (t >= nlead && t < tail0) {
+      t = tail0 - 1;                     // skip the untouched middle
+    }
+  }
+  double yb[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) yb[c] = Y[ridx(g.nhat + c)] - acc[c];
+  const double* Si = b.Sinv + (long long)sys * NB * NB;
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) s += Si[r * NB + c] * yb[c];
+    xb[r] = s;
+  }
+}
+
+// ---- backward substitution: U x = y - W x_b ; k_i = x - sum cfac_j k_j ;
+//      last stage: U_new = U + sum b_i k_i and the embedded error estimate
+template <int NPREV, int LAST>
+__device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stage& st) {
+  __shared__ double smem[(MAXW + 1) * KMAX];
+  __shared__ double s_err[MAXW];
   int sys, tile;
   resolve_tile(g, b, sys, tile);
-  const int lane_l = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int blk_l = tile * WARPS + warp;           // logical (reversed) block
+  const int lane_l = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int blk_l = tile * nwarps + warp;           // logical (reversed) block
   const bool active = blk_l < g.nblk;
   const int blk = g.nblk - 1 - blk_l;
   const int lane = 31 - lane_l;
   const int chunk = blk * 32 + lane;
   const long long vs = vstride(g);
-  double Uf[C][BETA + 1], y[C], x[C];
+  const long long cb = ((long long)blk * C) * 32 + lane;
+  const double* Ug = b.Uf + sys * vs * (BETA + 1) + cb * (BETA + 1) - (long long)lane * BETA;
+  const double* Y = b.Y + sys * vs + cb;
+  const int r0 = chunk * C;
+  const int wlead = b.lead[sys * 2 + 0];
+  const bool flagged = active && (r0 < wlead || (r0 + C > g.nhat - NB && r0 < g.nhat + NB));
+  const double* W = b.Wb + sys * vs * NB + cb * NB - (long long)lane * (NB - 1);
+  double xb[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) xb[c] = 0.0;
+  auto load_y = [&](int r) -> double {
+    double yv = Y[(long long)r * 32];
+    if (flagged) {
+      const int gr = r0 + r;
+      if (fill_row(gr, wlead, g)) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) yv -= W[((long long)r * NB + c) * 32] * xb[c];
+      } else if (gr >= g.nhat && gr < g.nhat + NB) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) if (gr - g.nhat == c) yv = xb[c];
+      }
+    }
+    return yv;
+  };
   Aff mine = Aff::identity();
   if (active) {
-    const double* Ug = b.Uf + sys * vs * (BETA + 1);
-    const double* Y = b.Y + sys * vs;
+    // border coupling of this chunk: y <- y - W x_b on fill rows, border rows <- x_b
+    // (applied on the fly in both passes; Y itself is left untouched because other
+    // threads still need y at the border rows)
+    if (flagged) border_solution(xb, g, b, sys, st.fwd_tiles, st.fwd_tile_rows);
+    RecState rs;
+    rs.init();
 #pragma unroll
-    for (int r = 0; r < C; ++r) {
+    for (int r = C - 1; r >= 0; --r) {
+      double coef[BETA];
 #pragma unroll
-      for (int q = 0; q <= BETA; ++q) Uf[r][q] = Ug[((long long)blk * C + r) * 32 * (BETA + 1) + q * 32 + lane];
-      y[r] = Y[((long long)blk * C + r) * 32 + lane];
+      for (int q = 0; q < BETA; ++q) coef[q] = Ug[((long long)r * (BETA + 1) + q + 1) * 32];
+      rs.step(coef, load_y(r), Ug[((long long)r * (BETA + 1)) * 32]);
     }
-    // border coupling
-    const int r0 = chunk * C;
-    const int wlead = b.lead[sys * 2 + 0];
-    if (r0 < wlead || (r0 + C > g.nhat - NB && r0 < g.nhat + NB)) {
-      const double* W = b.Wb + sys * vs * NB;
-      double xb[NB];
-#pragma unroll
-      for (int c = 0; c < NB; ++c) xb[c] = b.xb[(long long)sys * NB + c];
-#pragma unroll
-      for (int r = 0; r < C; ++r) {
-        const int gr = r0 + r;
-        if (gr < wlead || (gr >= g.nhat - NB && gr < g.nhat)) {
-          double s = y[r];
-#pragma unroll
-          for (int c = 0; c < NB; ++c) s -= W[((long long)blk * C + r) * 32 * NB + c * 32 + lane] * xb[c];
-          y[r] = s;
-        } else if (gr >= g.nhat && gr < g.nhat + NB) {
-#pragma unroll
-          for (int c = 0; c < NB; ++c) if (gr - g.nhat == c) y[r] = xb[c];
-        }
-      }
-    }
-    double s0[BETA];
-#pragma unroll
-    for (int t = 0; t < BETA; ++t) s0[t] = 0.0;
-    tfb::bwd_chunk<BETA, C>(Uf, y, s0, x);
-    tfb::bwd_map<BETA, C>(Uf, x, mine);
+    rs.to_map(mine);
   }
   const Aff pre = tile_scan<Aff>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
-                                 Aff::identity(), nullptr);
-  if (active) {
-    tfb::bwd_chunk<BETA, C>(Uf, y, pre.c(), x);
-    double* Kout = b.K[st.istage] + sys * vs;
-#pragma unroll
-    for (int r = 0; r < C; ++r) {
-      const long long a = ((long long)blk * C + r) * 32 + lane;
-      double k = x[r];
-#pragma unroll
-      for (int q = 0; q < MAXS; ++q)
-        if (q < st.nprev) k -= st.cfac[q] * b.K[q][sys * vs + a];
-      Kout[a] = k;
-    }
-  }
-}
-
-// ---- U_new = U + sum b_i k_i ; err = || U_new - (U_new + sum bp_i k_i) ||_inf ; Dirichlet hook
-extern "C" __global__ void __launch_bounds__(256) tf_k_update(Geom g, Buf b, Update up) {
-  const long long vs = vstride(g);
-  const int sys = blockIdx.y;
-  const double* U = b.U + sys * vs;
-  double* Un = b.Un + sys * vs;
+                                 g.epoch, Aff::identity(), nullptr);
   double emax = 0.0;
-  for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < vs;
-       a += (long long)gridDim.x * blockDim.x) {
-    double acc = 0.0, accp = 0.0;
+  const bool last = LAST < 0 ? (st.is_last != 0) : (LAST != 0);
+  if (active) {
+    double sv[BETA];
 #pragma unroll
-    for (int q = 0; q < MAXS; ++q)
-      if (q < up.s) {
-        const double k = b.K[q][sys * vs + a];
-        const double t = __dmul_rn(up.b[q], k);
-        acc = (q == 0) ? t : __dadd_rn(acc, t);
-        if (up.has_pred) {
-          const double tp = __dmul_rn(up.bp[q], k);
-          accp = (q == 0) ? tp : __dadd_rn(accp, tp);
+    for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
+    double* Kout = b.K[st.istage] + sys * vs + cb;
+#pragma unroll
+    for (int r = C - 1; r >= 0; --r) {
+      double v = load_y(r);
+#pragma unroll
+      for (int q = 0; q < BETA; ++q) v -= Ug[((long long)r * (BETA + 1) + q + 1) * 32] * sv[q];
+      v *= Ug[((long long)r * (BETA + 1)) * 32];
+#pragma unroll
+      for (int q = BETA - 1; q > 0; --q) sv[q] = sv[q - 1];
+      sv[0] = v;
+      const long long a = cb + (long long)r * 32;
+      double k = v;
+      constexpr int NQ = NPREV < 0 ? MAXS : NPREV;
+      double kprev[NQ > 0 ? NQ : 1];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (NPREV >= 0 || q < st.nprev) { kprev[q] = b.K[q][sys * vs + a]; k -= st.cfac[q] * kprev[q]; }
+      if (!last) {
+        Kout[(long long)r * 32] = k;
+      } else {
+        // U + ((b0 k0 + b1 k1) + ...) in the reference's summation order (schemes.py:164-170)
+        double acc = 0.0, accp = 0.0;
+#pragma unroll
+        for (int q = 0; q <= NQ && q < MAXS; ++q)
+          if (NPREV >= 0 || q <= st.nprev) {
+            const double kq = (q < (NPREV < 0 ? st.nprev : NPREV)) ? kprev[q < NQ ? q : 0] : k;
+            const double t = __dmul_rn(st.b[q], kq);
+            acc = (q == 0) ? t : __dadd_rn(acc, t);
+            const double tp = __dmul_rn(st.bp[q], kq);
+            accp = (q == 0) ? tp : __dadd_rn(accp, tp);
+          }
+        const double un = __dadd_rn(b.U[sys * vs + a], acc);
+        b.Un[sys * vs + a] = un;
+        if (st.has_pred) {
+          const double e = fabs(__dsub_rn(un, __dadd_rn(un, accp)));
+          emax = (e > emax || e != e) ? e : emax;
         }
       }
-    double un = __dadd_rn(U[a], acc);
-    if (up.has_pred) {
-      const double e = fabs(__dsub_rn(un, __dadd_rn(un, accp)));
-      // padding unknowns carry zeros: no contribution
-      emax = (e > emax || e != e) ? e : emax;
     }
-    Un[a] = un;
   }
-  if (up.has_pred) {
+  if (last && st.has_pred) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
       const double o = __shfl_xor_sync(0xffffffffu, emax, d);
       emax = (o > emax || o != o) ? o : emax;
     }
-    if ((threadIdx.x & 31) == 0)
+    if (lane_l == 0) s_err[warp] = emax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < nwarps; ++w) emax = (s_err[w] > emax || s_err[w] != s_err[w]) ? s_err[w] : emax;
       atomicMax((unsigned long long*)(b.err + sys), (unsigned long long)__double_as_longlong(emax));
+    }
   }
 }
+
+#define TF_BWD_KERNEL(name, NP, LS)                                                      \
+  extern "C" __global__ void __launch_bounds__(NT, TF_MINB) name(Geom g, Buf b, Stage st) { \
+    bwd_body<NP, LS>(g, b, st);                                                           \
+  }
+TF_BWD_KERNEL(tf_k_bwd0n, 0, 0)
+TF_BWD_KERNEL(tf_k_bwd0l, 0, 1)
+TF_BWD_KERNEL(tf_k_bwd1n, 1, 0)
+TF_BWD_KERNEL(tf_k_bwd1l, 1, 1)
+TF_BWD_KERNEL(tf_k_bwd2l, 2, 1)
+TF_BWD_KERNEL(tf_k_bwdg, -1, -1)
 
 // Dirichlet-style hook: U[var][0] = left, U[var][N-1] = right  (README.md:126-129)
 extern "C" __global__ void tf_k_dirichlet(Geom g, double* __restrict__ U, const double* __restrict__ dir,

@@ -47,23 +47,17 @@ TF_HD TF_INLINE double TF_MIN(double a, double b) { return (a <= b || a != a) ? 
 TF_HD TF_INLINE double TF_SIGN(double a) { return a > 0 ? 1.0 : (a < 0 ? -1.0 : a); }
 
 // Division by a uniform constant cst[j].  Exact mode: a true IEEE division.
-// Fast mode (-DTF_FAST_DIV=1): q0 = a*rc; r = fma(-q0, c, a); q = fma(r, rc, q0)
+// Fast mode (template argument TF_FD = true): q0 = a*rc; r = fma(-q0, c, a); q = fma(r, rc, q0)
 // with rc = RN(1/c) from the host table (entry TF_NCONST + j).  The residual r is
 // exact, so q is the correctly rounded quotient except when a/c lies within
 // ~2^-105 (relative) of a rounding boundary, where it may be off by one ulp.
-#ifndef TF_FAST_DIV
-#define TF_FAST_DIV 0
-#endif
-#if TF_FAST_DIV
 TF_HD TF_INLINE double tf_fdiv(double a, double c, double rc) {
   const double q0 = TF_MUL(a, rc);
   const double r = TF_FMA(-q0, c, a);
   return TF_FMA(r, rc, q0);
 }
-#define TF_DIVC(a, j) tf_fdiv((a), cst[(j)], cst[TF_NCONST + (j)])
-#else
-#define TF_DIVC(a, j) TF_DIV((a), cst[(j)])
-#endif
+// TF_FD is the bool template parameter of the generated tf_model_F / tf_model_J
+#define TF_DIVC(a, j) (TF_FD ? tf_fdiv((a), cst[(j)], cst[TF_NCONST + (j)]) : TF_DIV((a), cst[(j)]))
 
 // One node's inputs: stencil window of every field (dependent variables first,
 // then helper functions), per-node parameter values, and x.

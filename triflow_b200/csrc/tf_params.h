@@ -12,6 +12,8 @@ struct TfGeom {
   int batch;    /* systems */
   int periodic;
   int nhat;     /* interior unknowns (N - P) * V */
+  int epoch;    /* look-back flag epoch of this launch */
+  unsigned ticket_base; /* value of the ticket counter when this launch starts */
 };
 
 struct TfBuf {
@@ -36,6 +38,7 @@ struct TfBuf {
   int* flags;           /* look-back: [0] ticket counter, then [batch*tiles] flags */
   double* lbagg;        /* [batch*tiles][KMAX] tile aggregates */
   double* lbinc;        /* [batch*tiles][KMAX] inclusive prefixes */
+  double* gpart;        /* [batch*fwd_tiles][NB] per-tile partial G^T y of the last fwd */
 };
 
 struct TfStage {
@@ -44,11 +47,11 @@ struct TfStage {
   double alpha[TF_MAXS];   /* U_i = U + sum alpha_j k_j */
   double cfac[TF_MAXS];    /* gamma_ij / gamma_ii */
   double dt;
-};
-
-struct TfUpdate {
-  int s;
+  int fwd_tiles;           /* tiling of the fwd launch (indexing of gpart) */
+  int fwd_tile_rows;
+  int is_last;             /* bwd of the last stage: write U_new and the error estimate */
   int has_pred;
   double b[TF_MAXS];
   double bp[TF_MAXS];
 };
+
