@@ -244,6 +244,7 @@ def run_gpu(args):
             "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(out))
+    D.finalize()
 
 
 # -------------------------------------------------------------- CPU baseline
@@ -271,12 +272,12 @@ def cpu_rate(workload, budget_s, cores):
     from triflow_b200.model import Model
     if workload == "ensemble":
         import multiprocessing as mp
-        N, steps = 4096, 10
+        N, steps = 4096, 20
         t0 = time.perf_counter()
         _cpu_member(("advdiff", 0, N, 2))
         per = (time.perf_counter() - t0) / 2
         nmem = max(cores, int(budget_s / max(per * steps, 1e-3)) * cores)
-        nmem = min(nmem, 64 * cores)
+        nmem = min(nmem, 512 * cores)
         jobs = [("advdiff", int(r), N, steps)
                 for r in np.linspace(0, W.ENSEMBLE_K * W.ENSEMBLE_C - 1, nmem)]
         t0 = time.perf_counter()

@@ -58,3 +58,8 @@ if __name__ == "__main__":
         for chunk in (4, 8, 16):
             run("advdiff", W.ensemble(4096, np.arange(8192)), lambda m: S.ROS3PRw(m, **fx),
                 batch=8192, chunk=chunk)
+    elif what == "ksens":
+        # 2^20 nodes as independent KS systems (no look-back) vs one long grid
+        for N, nb in ((4096, 256), (3072, 342), (2048, 512), (65536, 16)):
+            c = W.kuramoto(N)
+            run("ks", c, lambda m: S.ROS3PRw(m, **fx), batch=nb)

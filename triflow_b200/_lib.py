@@ -75,8 +75,9 @@ def build_cubin(header, chunk_nodes, warps, fast_div=False):
     os.makedirs(CACHE, exist_ok=True)
     digest = _sources_digest([os.path.join(CSRC, s) for s in _KERNEL_SRCS])
     minb = int(os.environ.get("TF_MINB", "2"))
-    key = hashlib.sha1(("%s|%s|%d|%d|%d" % (header, digest, chunk_nodes, minb,
-                                            int(fast_div))).encode()).hexdigest()[:20]
+    extra = os.environ.get("TF_CFLAGS", "").split()          # tuning knobs (-DTF_...)
+    key = hashlib.sha1(("%s|%s|%d|%d|%d|%s" % (header, digest, chunk_nodes, minb,
+                                               int(fast_div), extra)).encode()).hexdigest()[:20]
     cubin = os.path.join(CACHE, "m_%s.cubin" % key)
     if os.path.exists(cubin):
         return cubin
@@ -87,7 +88,7 @@ def build_cubin(header, chunk_nodes, warps, fast_div=False):
     tmp = cubin + ".tmp%d" % os.getpid()
     cmd = [_nvcc(), *ARCH, "-O3", "-std=c++17", "-lineinfo", "-I", CSRC,
            "-DTF_M=%d" % chunk_nodes, "-DTF_FAST_DIV=%d" % int(fast_div),
-           "-DTF_MINB=%d" % minb, "-cubin", "-o", tmp, src]
+           "-DTF_MINB=%d" % minb, *extra, "-cubin", "-o", tmp, src]
     subprocess.check_call(cmd)
     os.replace(tmp, cubin)
     return cubin

@@ -271,6 +271,38 @@ struct ChunkLU {
       }
     }
   }
+
+  // Same elimination, additionally returning the update X_out left on the next
+  // block.  The BETA extra rows must hold only their entries in columns < C (zeros
+  // elsewhere), so that after the elimination they hold -X_out.
+  TF_HD static TF_INLINE void run2x(const double (&A)[RT][W], const double* X,
+                                    double (&Uf)[C][BETA + 1], double (&Lown)[C][BETA],
+                                    double (&Lnext)[BETA][BETA], double* Xout, int& bad) {
+    double T[RT][W];
+    TF_UNROLL for (int r = 0; r < RT; ++r)
+      TF_UNROLL for (int j = 0; j < W; ++j) T[r][j] = A[r][j];
+    TF_UNROLL for (int a = 0; a < BETA; ++a)
+      TF_UNROLL for (int b = 0; b < BETA; ++b) T[a][BETA + b - a] -= X[a * BETA + b];
+    TF_UNROLL for (int r = 0; r < C; ++r)
+      TF_UNROLL for (int q = 0; q < BETA; ++q) Lown[r][q] = 0.0;
+    TF_UNROLL for (int a = 0; a < BETA; ++a)
+      TF_UNROLL for (int q = 0; q < BETA; ++q) Lnext[a][q] = 0.0;
+    TF_UNROLL for (int k = 0; k < C; ++k) {
+      const double piv = T[k][BETA];
+      if (!(piv != 0.0) || !(fabs(piv) < 1e300)) bad = 1;
+      const double inv = 1.0 / piv;
+      Uf[k][0] = inv;
+      TF_UNROLL for (int c = 1; c <= BETA; ++c) Uf[k][c] = T[k][BETA + c];
+      TF_UNROLL for (int r = k + 1; r < RT && r <= k + BETA; ++r) {
+        const double l = T[r][BETA + k - r] * inv;
+        if (r < C) Lown[r][r - k - 1] = l; else Lnext[r - C][r - k - 1] = l;
+        TF_UNROLL for (int c = k + 1; c <= k + BETA; ++c)
+          if (c - r >= -BETA && c - r <= BETA) T[r][BETA + c - r] -= l * T[k][BETA + c - k];
+      }
+    }
+    TF_UNROLL for (int a = 0; a < BETA; ++a)
+      TF_UNROLL for (int b = 0; b < BETA; ++b) Xout[a * BETA + b] = -T[C + a][BETA + b - a];
+  }
 };
 
 // ------------------------------------------------------ substitution recurrences

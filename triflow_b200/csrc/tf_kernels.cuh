@@ -48,7 +48,13 @@ constexpr int MAXW = TF_MAXW;
 constexpr int NT = 32 * MAXW;         // launch bound of the tile kernels
 constexpr bool FD = TF_FAST_DIV != 0;  // fast division by uniform constants in the solver path
 // the factor kernel keeps whole band rows in registers: fewer threads per CTA for wide bands
-constexpr int NT_FACTOR = (TF_P * TF_NVAR + TF_NVAR - 1) <= 1 ? 512 : 256;
+#ifndef TF_FACTOR_NT
+#define TF_FACTOR_NT (((TF_P * TF_NVAR + TF_NVAR - 1) <= 1) ? 512 : 256)
+#endif
+#ifndef TF_FACTOR_MINB
+#define TF_FACTOR_MINB 2
+#endif
+constexpr int NT_FACTOR = TF_FACTOR_NT;
 constexpr int WB = 2 * BETA + 1;
 constexpr int EX = (BETA + V - 1) / V;             // extra nodes needed from the next chunk
 constexpr int NF = TF_NFIELD;
@@ -141,8 +147,15 @@ __device__ __forceinline__ Mon warp_reduce_rev(Mon v, int lane) {
   return v;
 }
 
+// flags are published with release and polled with acquire semantics (gpu scope):
+// orders the payload written by the same thread without a full fence / L1 flush
 __device__ __forceinline__ int ld_flag(const int* p) {
-  return *((const volatile int*)p);
+  int v;
+  asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag(int* p, int v) {
+  asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // "absorbing" maps: composing anything earlier in front of them changes nothing
@@ -181,16 +194,14 @@ __device__ Mon lookback(const Mon& aggregate, const Buf& b, long long gbase, int
     if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < Mon::K; ++k) inc[k] = aggregate.d[k];
-      __threadfence();
-      *((volatile int*)(flags + tile)) = FI;
+      st_flag(flags + tile, FI);
     }
     return Mon::identity();
   }
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < Mon::K; ++k) agg[k] = aggregate.d[k];
-    __threadfence();
-    *((volatile int*)(flags + tile)) = FA;
+    st_flag(flags + tile, FA);
   }
   Mon prefix = Mon::identity();
   int look = tile - 1;
@@ -209,7 +220,6 @@ __device__ Mon lookback(const Mon& aggregate, const Buf& b, long long gbase, int
           while (f != FA && f != FI) f = ld_flag(flags + t);
         }
       }
-      __threadfence();
       const bool ready = (t < 0) || f == FA || f == FI;
       const unsigned mr = __ballot_sync(0xffffffffu, ready);
       const unsigned m2 = __ballot_sync(0xffffffffu, ready && (t < 0 || f == FI));
@@ -240,8 +250,7 @@ done:
     const Mon incl = Mon::combine(prefix, aggregate);
 #pragma unroll
     for (int k = 0; k < Mon::K; ++k) inc[k] = incl.d[k];
-    __threadfence();
-    *((volatile int*)(flags + tile)) = FI;
+    st_flag(flags + tile, FI);
   }
   return prefix;
 }
@@ -583,7 +592,7 @@ extern "C" __global__ void __launch_bounds__(256) tf_k_eval_J(Geom g, Buf b, dou
 }
 
 // ---- factor: A = I - a*J(U) -> banded LU (chunk scan with linear-fractional maps)
-extern "C" __global__ void __launch_bounds__(NT_FACTOR) tf_k_factor(Geom g, Buf b, double a) {
+__device__ __forceinline__ void factor_body_rows(const Geom& g, const Buf& b, double a) {
   __shared__ double smem[(MAXW + 1) * KMAX];
   int sys, tile;
   resolve_tile(g, b, sys, tile);
@@ -591,7 +600,10 @@ extern "C" __global__ void __launch_bounds__(NT_FACTOR) tf_k_factor(Geom g, Buf 
   const int blk = tile * nwarps + warp;
   const bool active = blk < g.nblk;
   const int chunk = blk * 32 + lane;
-  const double* cst = b.cst + (long long)sys * NC2;
+  __shared__ double s_cst[NC2];
+  for (int k = threadIdx.x; k < NC2; k += blockDim.x) s_cst[k] = b.cst[(long long)sys * NC2 + k];
+  __syncthreads();
+  const double* cst = s_cst;
   if (tile == 0 && threadIdx.x == 0) b.err[sys] = 0.0;     // consumed by the last bwd
   double A[C + BETA][WB];
   Star mine = Star::identity();
@@ -628,6 +640,191 @@ extern "C" __global__ void __launch_bounds__(NT_FACTOR) tf_k_factor(Geom g, Buf 
     }
     if (bad) atomicOr(b.status + sys, 1);
   }
+}
+
+// ---- streaming factorisation for scalar models (V == 1: rows == nodes, BETA == P).
+// The chunk is walked in sub-blocks of BETA rows.  Pass 1 carries the chunk's
+// linear-fractional map (P,Q,R,S) through the sub-blocks -- block elimination with a
+// symbolic incoming update -- keeping O(BETA^2) state; pass 2 re-evaluates the rows
+// (J is cheap) and does the scalar elimination with the true incoming update,
+// writing L and U as it goes.  No row storage, hence few registers.
+template <int NODES>
+__device__ __forceinline__ void node_row(double (&row)[WB], const double (&win)[NF][NODES + 2 * P],
+                                         int m, int i0, const Geom& g, const Buf& b, int sys, double a,
+                                         const double* cst) {
+  const int i = i0 + m;
+  const int npad = g.nblk * 32 * M;
+#pragma unroll
+  for (int d = 0; d < WB; ++d) row[d] = 0.0;
+  if (i >= npad) return;                          // beyond the system: no coupling
+  double jv[NNZ];
+  if (i < g.N) {
+    TfNodeIn in;
+    node_inputs<NODES>(in, win, m, i, g, b, sys);
+    tf_model_J<FD>(cst, in, jv);
+  }
+  if (i >= P && i < g.N - 2 * P) {
+    row[BETA] = 1.0;
+#pragma unroll
+    for (int kk = 0; kk < NNZ; ++kk) {
+      const int d = tf_j_off(kk);
+      const double s = __dmul_rn(a, jv[kk]);
+      row[BETA + d] = (d == 0) ? __dsub_rn(1.0, s) : -s;
+    }
+  } else {
+    double tmp[WB];
+    assemble_special(i, g, jv, a, tmp, b.btab + (long long)sys * 5 * NB * NB);
+#pragma unroll
+    for (int d = 0; d < WB; ++d) row[d] = tmp[d];
+  }
+}
+
+__device__ __forceinline__ void factor_body_stream(const Geom& g, const Buf& b, double a) {
+  static_assert(V == 1 || true, "");
+  constexpr int NODES = M + EX;
+  constexpr int NSB = C / BETA;                   // sub-blocks per chunk
+  __shared__ double smem[(MAXW + 1) * KMAX];
+  __shared__ double s_cst[NC2];
+  int sys, tile;
+  resolve_tile(g, b, sys, tile);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int blk = tile * nwarps + warp;
+  const bool active = blk < g.nblk;
+  const int chunk = blk * 32 + lane;
+  const int i0 = chunk * M;
+  for (int k = threadIdx.x; k < NC2; k += blockDim.x) s_cst[k] = b.cst[(long long)sys * NC2 + k];
+  __syncthreads();
+  const double* cst = s_cst;
+  if (tile == 0 && threadIdx.x == 0) b.err[sys] = 0.0;     // consumed by the last bwd
+  double win[NF][NODES + 2 * P];
+  Star mine = Star::identity();
+  int bad = 0;
+  if (active) {
+    load_windows<NODES, 0>(win, i0, g, b, sys, nullptr);
+    double cur[BETA][WB], nxt[BETA][WB];
+#pragma unroll
+    for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, b, sys, a, cst);
+#pragma unroll
+    for (int k = 0; k < NSB; ++k) {
+#pragma unroll
+      for (int r = 0; r < BETA; ++r) node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, b, sys, a, cst);
+      // Dh = D_k - P ; solve Dh [Z1 | Z2] = [C_k | Q]
+      double Dh[BETA * BETA], Z[BETA * 2 * BETA], Rr[BETA * BETA];
+#pragma unroll
+      for (int r = 0; r < BETA; ++r)
+#pragma unroll
+        for (int c = 0; c < BETA; ++c) {
+          Dh[r * BETA + c] = cur[r][BETA + c - r] - mine.P()[r * BETA + c];
+          Z[r * 2 * BETA + c] = (c <= r) ? cur[r][BETA + BETA + c - r] : 0.0;      // C_k
+          Z[r * 2 * BETA + BETA + c] = mine.Q()[r * BETA + c];
+          Rr[r * BETA + c] = (c >= r) ? nxt[r][BETA + c - BETA - r] : 0.0;          // R_k
+        }
+      tfb::solve_inplace<BETA, 2 * BETA>(Dh, Z);
+      double Z1[BETA * BETA], Z2[BETA * BETA];
+#pragma unroll
+      for (int r = 0; r < BETA; ++r)
+#pragma unroll
+        for (int c = 0; c < BETA; ++c) {
+          Z1[r * BETA + c] = Z[r * 2 * BETA + c];
+          Z2[r * BETA + c] = Z[r * 2 * BETA + BETA + c];
+        }
+      Star nx;
+      tfb::mm<BETA>(Rr, Z1, nx.P());
+      tfb::mm<BETA>(Rr, Z2, nx.Q());
+#pragma unroll
+      for (int q = 0; q < BETA * BETA; ++q) nx.R()[q] = mine.R()[q];
+      tfb::mma<BETA>(mine.S(), Z2, nx.R());
+      tfb::mm<BETA>(mine.S(), Z1, nx.S());
+      mine = nx;
+#pragma unroll
+      for (int r = 0; r < BETA; ++r)
+#pragma unroll
+        for (int d = 0; d < WB; ++d) cur[r][d] = nxt[r][d];
+    }
+#pragma unroll
+    for (int q = 0; q < Star::K; ++q)
+      if (!(fabs(mine.d[q]) < 1e300)) bad = 1;
+  }
+  const Star pre = tile_scan<Star>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
+                                   g.epoch, Star::identity(), nullptr);
+  if (active) {
+    double X[BETA * BETA];
+#pragma unroll
+    for (int q = 0; q < BETA * BETA; ++q) X[q] = pre.P()[q];
+    double* Lg = b.Lf + sys * vstride(g) * BETA;
+    double* Ug = b.Uf + sys * vstride(g) * (BETA + 1);
+    double Lprev[BETA][BETA];
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int q = 0; q < BETA; ++q) Lprev[r][q] = 0.0;
+    double cur[BETA][WB], nxt[BETA][WB];
+#pragma unroll
+    for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, b, sys, a, cst);
+#pragma unroll
+    for (int k = 0; k < NSB; ++k) {
+#pragma unroll
+      for (int r = 0; r < BETA; ++r) node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, b, sys, a, cst);
+      // window: rows of block k, then the sub-diagonal part of block k+1's rows
+      double A2[2 * BETA][WB];
+#pragma unroll
+      for (int r = 0; r < BETA; ++r)
+#pragma unroll
+        for (int d = 0; d < WB; ++d) {
+          A2[r][d] = cur[r][d];
+          // row BETA + r, column offset d - BETA: keep columns < BETA (block k) only
+          A2[BETA + r][d] = (BETA + r + d - BETA < BETA) ? nxt[r][d] : 0.0;
+        }
+      double Uf[BETA][BETA + 1], Lown[BETA][BETA], Lnext[BETA][BETA], Xo[BETA * BETA];
+      tfb::ChunkLU<BETA, BETA>::run2x(A2, X, Uf, Lown, Lnext, Xo, bad);
+#pragma unroll
+      for (int r = 0; r < BETA; ++r) {
+        const int row = k * BETA + r;
+#pragma unroll
+        for (int q = 0; q <= BETA; ++q)
+          Ug[((long long)blk * C + row) * 32 * (BETA + 1) + q * 32 + lane] = Uf[r][q];
+#pragma unroll
+        for (int q = 1; q <= BETA; ++q) {
+          const long long o = ((long long)blk * C + row) * 32 * BETA + (q - 1) * 32 + lane;
+          if (q <= r) Lg[o] = Lown[r][q - 1];
+          else if (k > 0) Lg[o] = Lprev[r][q - 1];
+          else if (chunk == 0) Lg[o] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < BETA; ++r)
+#pragma unroll
+        for (int q = 0; q < BETA; ++q) Lprev[r][q] = Lnext[r][q];
+#pragma unroll
+      for (int q = 0; q < BETA * BETA; ++q) X[q] = Xo[q];
+#pragma unroll
+      for (int r = 0; r < BETA; ++r)
+#pragma unroll
+        for (int d = 0; d < WB; ++d) cur[r][d] = nxt[r][d];
+    }
+    const int nchunk = chunk + 1;
+    if (nchunk < g.nblk * 32) {
+      const int nb = nchunk >> 5, nl = nchunk & 31;
+#pragma unroll
+      for (int r = 0; r < BETA; ++r)
+#pragma unroll
+        for (int q = r + 1; q <= BETA; ++q)
+          Lg[((long long)nb * C + r) * 32 * BETA + (q - 1) * 32 + nl] = Lprev[r][q - 1];
+    }
+    if (bad) atomicOr(b.status + sys, 1);
+  }
+}
+
+#ifndef TF_FACTOR_STREAM
+#define TF_FACTOR_STREAM (TF_NVAR == 1)
+#endif
+extern "C" __global__ void __launch_bounds__(NT_FACTOR, TF_FACTOR_MINB) tf_k_factor(Geom g, Buf b, double a) {
+#if TF_FACTOR_STREAM
+  if constexpr (V == 1 && C % BETA == 0) factor_body_stream(g, b, a);
+  else factor_body_rows(g, b, a);
+#else
+  factor_body_rows(g, b, a);
+#endif
 }
 
 // ---- border fill.  The last P nodes ("border", NB unknowns) are ordered last:
@@ -833,6 +1030,44 @@ __device__ __forceinline__ bool fill_row(int gr, int lead, const Geom& g) {
 
 // ---- forward substitution of one stage: rhs = dt*F(U_i) + sum cfac_j k_j ; L y = rhs
 //      + per-tile partial sums of G^T y for the border solve
+// ---- bulk asynchronous copies (TMA, cp.async.bulk) of a CTA's tile into shared memory.
+// A tile is one contiguous byte range in the lane-transposed layout, so the whole
+// tile is requested by one thread with one instruction per array and lands while
+// the other threads do index work; completion is signalled on an mbarrier.
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
+                                         unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TF_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TF_DONE;\n"
+      "bra TF_WAIT;\n"
+      "TF_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+
 // Streaming recurrences: only the last BETA values of the solution and of the BETA
 // homogeneous solutions are kept, so the register footprint is O(BETA^2) and the
 // factor rows are consumed as they arrive; the second pass re-reads them (L1/L2 hits).
@@ -881,22 +1116,69 @@ template <int NPREV>
 __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stage& st) {
   __shared__ double smem[(MAXW + 1) * KMAX];
   __shared__ double s_part[MAXW][NB];
-  extern __shared__ double s_f[];                 // [C][blockDim.x] right-hand side stash
+  __shared__ __align__(8) unsigned long long s_bar;
+  extern __shared__ __align__(128) double dsm[];
   int sys, tile;
   resolve_tile(g, b, sys, tile);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int blk = tile * nwarps + warp;
-  const bool active = blk < g.nblk;
+  const int T = blockDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
+  double* sL = dsm;                        // [T*C*BETA] L rows of the tile (TMA)
+  double* sS = dsm + (size_t)T * C * BETA; // [T*C]      stage state of the tile (halo sharing),
+  double* sF = sS;                         //            reused as right-hand side stash
+  const int blk0 = tile * nwarps;
+  const int nact = (g.nblk - blk0) < nwarps ? (g.nblk - blk0) : nwarps;   // active warp-blocks
+  const int blk = blk0 + warp;
+  const bool active = warp < nact;
   const int chunk = blk * 32 + lane;
   const int i0 = chunk * M;
-  const double* cst = b.cst + (long long)sys * NC2;
+  __shared__ double s_cst[NC2];                                   // uniform constants of the system
+  const double* cst = s_cst;
   const long long vs = vstride(g);
   const long long cb = ((long long)blk * C) * 32 + lane;          // own chunk, element 0
-  const double* Lg = b.Lf + sys * vs * BETA + cb * BETA - (long long)lane * (BETA - 1);
-  Aff mine = Aff::identity();
+  const int sb = (warp * C) * 32 + lane;                          // same, inside the tile
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  for (int k = threadIdx.x; k < NC2; k += blockDim.x) s_cst[k] = b.cst[(long long)sys * NC2 + k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned bytes = (unsigned)(nact * C * 32 * BETA * sizeof(double));
+    mbar_expect_tx(&s_bar, bytes);
+    bulk_g2s(sL, b.Lf + (sys * vs + (long long)blk0 * C * 32) * BETA, bytes, &s_bar);
+  }
+  // own stage state -> registers -> shared (neighbours read their halo from there)
+  double own[C];
   if (active) {
-    double win[NF][M + 2 * P];
-    load_windows<M, NPREV>(win, i0, g, b, sys, &st);
+    const double* U = b.U + sys * vs;
+#pragma unroll
+    for (int r = 0; r < C; ++r) own[r] = stage_value<NPREV>(U, b, sys * vs, cb + (long long)r * 32, &st);
+#pragma unroll
+    for (int r = 0; r < C; ++r) sS[sb + r * 32] = own[r];
+  }
+  __syncthreads();
+  Aff mine = Aff::identity();
+  double win[NF][M + 2 * P];
+  if (active) {
+    const bool interior = i0 >= P && i0 + M + P <= g.N && P <= M && NH == 0 &&
+                          chunk > blk0 * 32 && chunk < (blk0 + nact) * 32 - 1;
+    if (interior) {
+#pragma unroll
+      for (int w = 0; w < M + 2 * P; ++w) {
+        const int rel = w - P;
+        const int dc = rel < 0 ? -1 : (rel >= M ? 1 : 0);
+        const int m = rel - dc * M;
+        // neighbour chunk inside the tile: lane +- 1, possibly in the adjacent warp-block
+        const int t2 = (int)threadIdx.x + dc;
+        const int nb = ((t2 >> 5) * C) * 32 + (t2 & 31);
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          win[e][w] = (dc == 0) ? own[(m * V + e) < C ? (m * V + e) : 0] : sS[nb + (m * V + e) * 32];
+      }
+    } else {
+      load_windows<M, NPREV>(win, i0, g, b, sys, &st);
+    }
+  }
+  __syncthreads();                         // every halo has been read: sS becomes sF
+  if (active) {
+    mbar_wait(&s_bar, 0);
     RecState rs;
     rs.init();
 #pragma unroll
@@ -918,10 +1200,10 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
         for (int q = 0; q < (NPREV < 0 ? MAXS : NPREV); ++q)
           if (NPREV >= 0 || q < st.nprev) rhs += st.cfac[q] * b.K[q][sys * vs + cb + (long long)r * 32];
         rhs = (i < g.N) ? rhs : 0.0;
-        s_f[r * blockDim.x + threadIdx.x] = rhs;
+        sF[sb + r * 32] = rhs;
         double coef[BETA];
 #pragma unroll
-        for (int q = 0; q < BETA; ++q) coef[q] = Lg[((long long)r * BETA + q) * 32];
+        for (int q = 0; q < BETA; ++q) coef[q] = sL[((warp * C + r) * BETA + q) * 32 + lane];
         rs.step(coef, rhs, 1.0);
       }
     }
@@ -946,9 +1228,9 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
     const int r0 = chunk * C;
 #pragma unroll
     for (int r = 0; r < C; ++r) {
-      double v = s_f[r * blockDim.x + threadIdx.x];
+      double v = sF[sb + r * 32];
 #pragma unroll
-      for (int q = 0; q < BETA; ++q) v -= Lg[((long long)r * BETA + q) * 32] * sv[q];
+      for (int q = 0; q < BETA; ++q) v -= sL[((warp * C + r) * BETA + q) * 32 + lane] * sv[q];
 #pragma unroll
       for (int q = BETA - 1; q > 0; --q) sv[q] = sv[q - 1];
       sv[0] = v;
@@ -1021,18 +1303,37 @@ template <int NPREV, int LAST>
 __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stage& st) {
   __shared__ double smem[(MAXW + 1) * KMAX];
   __shared__ double s_err[MAXW];
+  __shared__ __align__(8) unsigned long long s_bar;
+  extern __shared__ __align__(128) double dsm[];
   int sys, tile;
   resolve_tile(g, b, sys, tile);
-  const int lane_l = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int blk_l = tile * nwarps + warp;           // logical (reversed) block
-  const bool active = blk_l < g.nblk;
-  const int blk = g.nblk - 1 - blk_l;
+  const int T = blockDim.x;
+  const int lane_l = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
+  double* sU = dsm;                               // [T*C*(BETA+1)] U rows of the tile (TMA)
+  // logical (reversed) blocks [tile*nwarps, +nact) are the actual blocks [bmin, bmin+nact)
+  const int bl0 = tile * nwarps;
+  const int nact = (g.nblk - bl0) < nwarps ? (g.nblk - bl0) : nwarps;
+  const int bmin = g.nblk - bl0 - nact;
+  const bool active = warp < nact;
+  const int blk = g.nblk - 1 - (bl0 + warp);
   const int lane = 31 - lane_l;
   const int chunk = blk * 32 + lane;
   const long long vs = vstride(g);
   const long long cb = ((long long)blk * C) * 32 + lane;
-  const double* Ug = b.Uf + sys * vs * (BETA + 1) + cb * (BETA + 1) - (long long)lane * BETA;
-  const double* Y = b.Y + sys * vs + cb;
+  const int sb = ((blk - bmin) * C) * 32 + lane;            // own chunk inside the tile
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned by = (unsigned)(nact * C * 32 * sizeof(double));
+    mbar_expect_tx(&s_bar, by * (BETA + 1));
+    bulk_g2s(sU, b.Uf + (sys * vs + (long long)bmin * C * 32) * (BETA + 1), by * (BETA + 1), &s_bar);
+  }
+  double yreg[C];
+  if (active) {
+    const double* Yg = b.Y + sys * vs + cb;
+#pragma unroll
+    for (int r = 0; r < C; ++r) yreg[r] = Yg[(long long)r * 32];
+  }
   const int r0 = chunk * C;
   const int wlead = b.lead[sys * 2 + 0];
   const bool flagged = active && (r0 < wlead || (r0 + C > g.nhat - NB && r0 < g.nhat + NB));
@@ -1040,8 +1341,11 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
   double xb[NB];
 #pragma unroll
   for (int c = 0; c < NB; ++c) xb[c] = 0.0;
+  // border coupling of this chunk: y <- y - W x_b on fill rows, border rows <- x_b
+  // (applied on the fly in both passes)
+  if (flagged) border_solution(xb, g, b, sys, st.fwd_tiles, st.fwd_tile_rows);
   auto load_y = [&](int r) -> double {
-    double yv = Y[(long long)r * 32];
+    double yv = yreg[r];
     if (flagged) {
       const int gr = r0 + r;
       if (fill_row(gr, wlead, g)) {
@@ -1054,27 +1358,25 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
     }
     return yv;
   };
+  const bool last = LAST < 0 ? (st.is_last != 0) : (LAST != 0);
+  constexpr int NQ = NPREV < 0 ? MAXS : NPREV;
   Aff mine = Aff::identity();
+  mbar_wait(&s_bar, 0);
   if (active) {
-    // border coupling of this chunk: y <- y - W x_b on fill rows, border rows <- x_b
-    // (applied on the fly in both passes; Y itself is left untouched because other
-    // threads still need y at the border rows)
-    if (flagged) border_solution(xb, g, b, sys, st.fwd_tiles, st.fwd_tile_rows);
     RecState rs;
     rs.init();
 #pragma unroll
     for (int r = C - 1; r >= 0; --r) {
       double coef[BETA];
 #pragma unroll
-      for (int q = 0; q < BETA; ++q) coef[q] = Ug[((long long)r * (BETA + 1) + q + 1) * 32];
-      rs.step(coef, load_y(r), Ug[((long long)r * (BETA + 1)) * 32]);
+      for (int q = 0; q < BETA; ++q) coef[q] = sU[sb * (BETA + 1) - lane * BETA + (r * (BETA + 1) + q + 1) * 32];
+      rs.step(coef, load_y(r), sU[sb * (BETA + 1) - lane * BETA + (r * (BETA + 1)) * 32]);
     }
     rs.to_map(mine);
   }
   const Aff pre = tile_scan<Aff>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
                                  g.epoch, Aff::identity(), nullptr);
   double emax = 0.0;
-  const bool last = LAST < 0 ? (st.is_last != 0) : (LAST != 0);
   if (active) {
     double sv[BETA];
 #pragma unroll
@@ -1084,14 +1386,13 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
     for (int r = C - 1; r >= 0; --r) {
       double v = load_y(r);
 #pragma unroll
-      for (int q = 0; q < BETA; ++q) v -= Ug[((long long)r * (BETA + 1) + q + 1) * 32] * sv[q];
-      v *= Ug[((long long)r * (BETA + 1)) * 32];
+      for (int q = 0; q < BETA; ++q) v -= sU[sb * (BETA + 1) - lane * BETA + (r * (BETA + 1) + q + 1) * 32] * sv[q];
+      v *= sU[sb * (BETA + 1) - lane * BETA + (r * (BETA + 1)) * 32];
 #pragma unroll
       for (int q = BETA - 1; q > 0; --q) sv[q] = sv[q - 1];
       sv[0] = v;
       const long long a = cb + (long long)r * 32;
       double k = v;
-      constexpr int NQ = NPREV < 0 ? MAXS : NPREV;
       double kprev[NQ > 0 ? NQ : 1];
 #pragma unroll
       for (int q = 0; q < NQ; ++q)

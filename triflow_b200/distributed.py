@@ -27,10 +27,19 @@ def init(backend=None):
         return rank, ws
     if backend is None:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
+    kw = {}
     if backend == "nccl":
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    dist.init_process_group(backend=backend, rank=rank, world_size=ws)
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        kw["device_id"] = torch.device("cuda", local)
+    dist.init_process_group(backend=backend, rank=rank, world_size=ws, **kw)
     return rank, ws
+
+
+def finalize():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def barrier():
