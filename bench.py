@@ -193,9 +193,16 @@ def run_gpu(args):
     peak, peak_src = peaks()
     achieved = kernel_bytes(wk, dom) * units / (dom_ms / dom_n * 1e-3) / 1e9
     step_gbs = wk["Q"] * units * args.steps / (ms.value * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            per_node = json.load(f).get(args.workload, {}).get(dom)
+        if per_node:
+            traffic = per_node * units          # DRAM bytes per launch (ncu, profiled kernel)
     roofline = {"bound": "hbm", "kernel": "tf_k_" + dom, "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "kernel_share_of_step": round(dom_ms / tot_ms, 3),
                 "step_achieved": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4),
                 "bytes_per_node_step": wk["Q"],
