@@ -288,3 +288,99 @@ def test_ks_full_size_linear_solve_residual():
     d = f1.uflat - f0.uflat
     res = d - dt * (J0 @ d) - dt * F0
     assert np.max(np.abs(res)) <= 1e-9 * np.max(np.abs(dt * F0))
+
+
+# ---------------------------------------------------------- more coverage
+@pytest.mark.parametrize("scheme", ["RODASPR", "ROS3PRL"])
+def test_generic_stage_kernels_many_tiles(scheme):
+    """Stages >= 3 go through the generic (run-time stage count) sweep kernels;
+    several look-back tiles."""
+    from oracle import schemes as O
+    from triflow_b200 import schemes as S, workloads as W
+    c = W.kuramoto(20000)
+    gm, om = gmodel("ks"), omodel("ks")
+    sg = run_fixed(gm, getattr(S, scheme)(gm, **FX), c, 3, 3)
+    f = om.fields_template(x=c["x"], **c["fields"])
+    t, sch = 0.0, getattr(O, scheme)(om, **FX)
+    for _ in range(3):
+        t, f = sch(t, f, c["dt"], c["pars"])
+    assert rel_traj_err(sg[-1], f.uflat) <= TRAJ_TOL
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+def test_per_node_parameter_in_scheme(periodic):
+    """Array-valued parameter (reference core/routines.py:40) through the solver path."""
+    from oracle import schemes as O
+    from triflow_b200 import schemes as S
+    rng = np.random.default_rng(3)
+    N = 3000
+    x = np.linspace(0, 10, N)
+    U = np.cos(2 * np.pi * x / 10) + 0.1 * rng.standard_normal(N)
+    pars = dict(k=1e-2 * (1 + rng.random(N)), c=.3, periodic=periodic)
+    gm, om = gmodel("advdiff"), omodel("advdiff")
+    c = dict(x=x, fields=dict(U=U), pars=pars, dt=0.01)
+    sg = run_fixed(gm, S.ROS3PRw(gm, **FX), c, 4, 4)
+    f = om.fields_template(x=x, U=U)
+    t, sch = 0.0, O.ROS3PRw(om, **FX)
+    for _ in range(4):
+        t, f = sch(t, f, 0.01, pars)
+    assert rel_traj_err(sg[-1], f.uflat) <= TRAJ_TOL
+
+
+def test_two_variable_dirichlet_hook():
+    from oracle import schemes as O
+    from triflow_b200 import schemes as S
+    N = 700
+    x = np.linspace(0, 10, N)
+    fields = dict(U=np.cos(x), V=np.sin(x))
+    pars = dict(k1=.1, k2=.05, c1=.3, c2=-.2, periodic=False)
+    hook = S.Dirichlet(U=(1.0, None), V=(None, -1.0))
+    gm, om = gmodel("coupled"), omodel("coupled")
+    c = dict(x=x, fields=fields, pars=pars, dt=0.02)
+    sg = run_fixed(gm, S.ROS3PRw(gm, **FX), c, 5, 5, hook=hook)
+    f = om.fields_template(x=x, **fields)
+    t, sch = 0.0, O.ROS3PRw(om, **FX)
+    for _ in range(5):
+        t, f = sch(t, f, 0.02, pars, hook=hook)
+    assert f["U"][0] == 1.0 and f["V"][-1] == -1.0
+    assert rel_traj_err(sg[-1], f.uflat) <= TRAJ_TOL
+
+
+def test_exact_division_mode_matches_too():
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.compiler import make_cuda_compiler
+    from triflow_b200.model import Model
+    c = W.kuramoto(2048)
+    m = Model(**W.model_args("ks"), compiler=make_cuda_compiler(fast_div=False))
+    snaps = run_fixed(m, S.ROS3PRw(m, **FX), c, 50, 10)
+    assert rel_traj_err(snaps, traj()["ks_2048"]) <= TRAJ_TOL
+
+
+def test_error_paths():
+    from triflow_b200 import schemes as S
+    m = gmodel("ks")
+    x = np.linspace(0, 1, 7)                       # smaller than 4*half_width + 1
+    f = m.fields_template(x=x, U=np.ones(7))
+    with pytest.raises(ValueError):
+        S.ROS2(m)(0.0, f, 0.1, dict(periodic=True))
+    with pytest.raises(ValueError):
+        S.Theta(m, solver=lambda A, b: b)
+    # singular system: dt huge with a sign making I - gamma*dt*J singular is model dependent;
+    # NaN input must surface as an error, not as silent garbage
+    x = np.linspace(0, 1, 300)
+    f = m.fields_template(x=x, U=np.full(300, np.nan))
+    with pytest.raises(RuntimeError):
+        S.ROS2(m)(0.0, f, 0.1, dict(periodic=True))
+
+
+def test_run_fixed_equals_repeated_calls():
+    from triflow_b200 import schemes as S, workloads as W
+    c = W.burgers(4096, 2)
+    m = gmodel(c["model"])
+    f0 = m.fields_template(x=c["x"], **c["fields"])
+    _, fa = S.ROS2(m).run_fixed(0.0, f0, c["dt"], 7, c["pars"])
+    fb, t = f0, 0.0
+    sch = S.ROS2(m)
+    for _ in range(7):
+        t, fb = sch(t, fb, c["dt"], c["pars"])
+    assert np.array_equal(fa.uflat, fb.uflat)
