@@ -116,6 +116,12 @@ int tf_scheme_advance(tf_state_t st, tf_scheme_t sc, double t, double dt, double
                       double safety_factor, int max_iter, double dt_min, int recompute_target,
                       double* internal_dt, int* n_fixed_steps, double* last_err);
 
+/* Optional: keep the factorisation across steps while gamma*dt is unchanged.  Only valid
+ * for models whose Jacobian does not depend on the state (linear models with uniform
+ * parameters; the reference rebuilds and refactorises every step regardless,
+ * core/schemes.py:146-149).  Off by default; uploading new constants invalidates it. */
+int tf_state_set_factor_reuse(tf_state_t st, int enable);
+
 /* status bits per system (bit0 bad pivot, bit1 singular border block) */
 int tf_state_status(tf_state_t st, int* status);
 /* number of kernels launched on this state's context since creation */

@@ -384,3 +384,23 @@ def test_run_fixed_equals_repeated_calls():
     for _ in range(7):
         t, fb = sch(t, fb, c["dt"], c["pars"])
     assert np.array_equal(fa.uflat, fb.uflat)
+
+
+def test_factor_reuse_is_bit_identical_for_constant_jacobian():
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.ensemble import Ensemble
+    mem = np.arange(0, 32768, 4099)
+    c = W.ensemble(1024, mem)
+    m = gmodel("advdiff")
+    out = []
+    for reuse in (False, True):
+        ens = Ensemble(m, S.ROS3PRw(m, **FX), c["x"], c["fields"], c["pars"],
+                       hook=S.Dirichlet(U=(1.0, 0.0)), batch=len(mem),
+                       reuse_constant_factor=reuse)
+        ens.step(c["dt"], 12)
+        out.append(ens.download())
+    assert np.array_equal(out[0], out[1])
+    with pytest.raises(ValueError):
+        km = gmodel("ks")
+        ck = W.kuramoto(1024)
+        Ensemble(km, S.ROS2(km), ck["x"], ck["fields"], ck["pars"], reuse_constant_factor=True)

@@ -309,6 +309,8 @@ def lower(model, node_pars=()):
     out.uniform_pars = tuple(q for q in model._pars if q not in node_pars)
     out.uses_x = uses_x
     out.stats = stats
+    out.jacobian_is_constant = (stats["J"]["ops"] == 0 and not node_pars and
+                                all("in." not in ln for ln in bodies["J"]))
     out.fields = fields
     out.header = _render_header(out, bodies)
     out.key = hashlib.sha1(out.header.encode()).hexdigest()[:16]

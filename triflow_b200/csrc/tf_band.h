@@ -37,6 +37,13 @@
 #define TF_UNROLL
 #endif
 
+// reciprocal of a pivot: correctly rounded, without the IEEE-division slow path
+#ifdef __CUDA_ARCH__
+#define TF_RCP(x) __drcp_rn(x)
+#else
+#define TF_RCP(x) (1.0 / (x))
+#endif
+
 namespace tfb {
 
 template <int A, int B> struct Min { static constexpr int v = A < B ? A : B; };
@@ -83,7 +90,7 @@ TF_HD TF_INLINE void solve_inplace(double* M, double* RHS) {
         RHS[r * NR + c] = sw ? a : b;
       }
     }
-    const double inv = 1.0 / M[k * N + k];
+    const double inv = TF_RCP(M[k * N + k]);
     TF_UNROLL for (int c = k + 1; c < N; ++c) M[k * N + c] *= inv;
     TF_UNROLL for (int c = 0; c < NR; ++c) RHS[k * NR + c] *= inv;
     TF_UNROLL for (int r = 0; r < N; ++r) {
@@ -205,7 +212,7 @@ struct ChunkLU {
     TF_UNROLL for (int k = 0; k < C; ++k) {
       const double piv = T[k][BETA];
       if (!(piv != 0.0) || !(fabs(piv) < 1e300)) bad = 1;
-      const double inv = 1.0 / piv;
+      const double inv = TF_RCP(piv);
       TF_UNROLL for (int r = k + 1; r < C && r <= k + BETA; ++r) {
         const double l = T[r][BETA + k - r] * inv;
         TF_UNROLL for (int c = k + 1; c < C && c <= k + BETA; ++c)
@@ -215,7 +222,7 @@ struct ChunkLU {
     }
     // back substitution
     TF_UNROLL for (int k = C - 1; k >= 0; --k) {
-      const double inv = 1.0 / T[k][BETA];
+      const double inv = TF_RCP(T[k][BETA]);
       TF_UNROLL for (int b = 0; b < 2 * BETA; ++b) {
         double s = Y[k][b];
         TF_UNROLL for (int c = k + 1; c < C && c <= k + BETA; ++c)
@@ -260,7 +267,7 @@ struct ChunkLU {
     TF_UNROLL for (int k = 0; k < C; ++k) {
       const double piv = T[k][BETA];
       if (!(piv != 0.0) || !(fabs(piv) < 1e300)) bad = 1;
-      const double inv = 1.0 / piv;
+      const double inv = TF_RCP(piv);
       Uf[k][0] = inv;
       TF_UNROLL for (int c = 1; c <= BETA; ++c) Uf[k][c] = T[k][BETA + c];
       TF_UNROLL for (int r = k + 1; r < RT && r <= k + BETA; ++r) {
@@ -290,7 +297,7 @@ struct ChunkLU {
     TF_UNROLL for (int k = 0; k < C; ++k) {
       const double piv = T[k][BETA];
       if (!(piv != 0.0) || !(fabs(piv) < 1e300)) bad = 1;
-      const double inv = 1.0 / piv;
+      const double inv = TF_RCP(piv);
       Uf[k][0] = inv;
       TF_UNROLL for (int c = 1; c <= BETA; ++c) Uf[k][c] = T[k][BETA + c];
       TF_UNROLL for (int r = k + 1; r < RT && r <= k + BETA; ++r) {

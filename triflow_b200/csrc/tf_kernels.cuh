@@ -651,13 +651,31 @@ __device__ __forceinline__ void factor_body_rows(const Geom& g, const Buf& b, do
 template <int NODES>
 __device__ __forceinline__ void node_row(double (&row)[WB], const double (&win)[NF][NODES + 2 * P],
                                          int m, int i0, const Geom& g, const Buf& b, int sys, double a,
-                                         const double* cst) {
+                                         const double* cst, bool all_regular) {
   const int i = i0 + m;
+  if (all_regular) {                              // whole chunk away from the domain ends
+    TfNodeIn in;
+    node_inputs<NODES>(in, win, m, i, g, b, sys);
+    double jv[NNZ];
+    tf_model_J<FD>(cst, in, jv);
+#pragma unroll
+    for (int d = 0; d < WB; ++d) row[d] = 0.0;
+    row[BETA] = 1.0;
+#pragma unroll
+    for (int kk = 0; kk < NNZ; ++kk) {
+      const int d = tf_j_off(kk);
+      const double s = __dmul_rn(a, jv[kk]);
+      row[BETA + d] = (d == 0) ? __dsub_rn(1.0, s) : -s;
+    }
+    return;
+  }
   const int npad = g.nblk * 32 * M;
 #pragma unroll
   for (int d = 0; d < WB; ++d) row[d] = 0.0;
   if (i >= npad) return;                          // beyond the system: no coupling
   double jv[NNZ];
+#pragma unroll
+  for (int kk = 0; kk < NNZ; ++kk) jv[kk] = 0.0;
   if (i < g.N) {
     TfNodeIn in;
     node_inputs<NODES>(in, win, m, i, g, b, sys);
@@ -672,8 +690,10 @@ __device__ __forceinline__ void node_row(double (&row)[WB], const double (&win)[
       row[BETA + d] = (d == 0) ? __dsub_rn(1.0, s) : -s;
     }
   } else {
-    double tmp[WB];
-    assemble_special(i, g, jv, a, tmp, b.btab + (long long)sys * 5 * NB * NB);
+    double jvl[NNZ], tmp[WB];                     // the rare path works on private copies
+#pragma unroll
+    for (int kk = 0; kk < NNZ; ++kk) jvl[kk] = jv[kk];
+    assemble_special(i, g, jvl, a, tmp, b.btab + (long long)sys * 5 * NB * NB);
 #pragma unroll
     for (int d = 0; d < WB; ++d) row[d] = tmp[d];
   }
@@ -699,15 +719,16 @@ __device__ __forceinline__ void factor_body_stream(const Geom& g, const Buf& b, 
   double win[NF][NODES + 2 * P];
   Star mine = Star::identity();
   int bad = 0;
+  const bool allreg = i0 >= P && i0 + NODES <= g.N - 2 * P;
   if (active) {
     load_windows<NODES, 0>(win, i0, g, b, sys, nullptr);
     double cur[BETA][WB], nxt[BETA][WB];
 #pragma unroll
-    for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, b, sys, a, cst);
+    for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, b, sys, a, cst, allreg);
 #pragma unroll
     for (int k = 0; k < NSB; ++k) {
 #pragma unroll
-      for (int r = 0; r < BETA; ++r) node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, b, sys, a, cst);
+      for (int r = 0; r < BETA; ++r) node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, b, sys, a, cst, allreg);
       // Dh = D_k - P ; solve Dh [Z1 | Z2] = [C_k | Q]
       double Dh[BETA * BETA], Z[BETA * 2 * BETA], Rr[BETA * BETA];
 #pragma unroll
@@ -760,11 +781,11 @@ __device__ __forceinline__ void factor_body_stream(const Geom& g, const Buf& b, 
       for (int q = 0; q < BETA; ++q) Lprev[r][q] = 0.0;
     double cur[BETA][WB], nxt[BETA][WB];
 #pragma unroll
-    for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, b, sys, a, cst);
+    for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, b, sys, a, cst, allreg);
 #pragma unroll
     for (int k = 0; k < NSB; ++k) {
 #pragma unroll
-      for (int r = 0; r < BETA; ++r) node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, b, sys, a, cst);
+      for (int r = 0; r < BETA; ++r) node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, b, sys, a, cst, allreg);
       // window: rows of block k, then the sub-diagonal part of block k+1's rows
       double A2[2 * BETA][WB];
 #pragma unroll
@@ -1211,11 +1232,12 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
   }
   const Aff pre = tile_scan<Aff>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
                                  g.epoch, Aff::identity(), nullptr);
-  // second pass with the true incoming state; partial G^T y of the tile on the fly
+  // second pass with the true incoming state; when the border fill of this step is
+  // already complete (every stage but the first) the tile also reduces its share of G^T y
   const int tile_rows = nwarps * 32 * C;
-  const int glead = b.lead[sys * 2 + 1];
+  const int glead = st.use_partials ? b.lead[sys * 2 + 1] : 0;
   const int t0 = tile * tile_rows, t1 = t0 + tile_rows;
-  const bool gtile = t0 < glead || (t1 > g.nhat - NB && t0 < g.nhat);
+  const bool gtile = st.use_partials && (t0 < glead || (t1 > g.nhat - NB && t0 < g.nhat));
   double acc[NB];
 #pragma unroll
   for (int c = 0; c < NB; ++c) acc[c] = 0.0;
@@ -1266,9 +1288,10 @@ TF_FWD_KERNEL(tf_k_fwd1, 1)
 TF_FWD_KERNEL(tf_k_fwd2, 2)
 TF_FWD_KERNEL(tf_k_fwdg, -1)
 
-// x_b = S^-1 (y_b - sum of the fwd tiles' partial G^T y), fixed summation order
-__device__ __forceinline__ void border_solution(double (&xb)[NB], const Geom& g, const Buf& b,
-                                                int sys, int fwd_tiles, int fwd_tile_rows) {
+// x_b from the per-tile partial sums the forward sweep left (fixed summation order);
+// cheap enough that every chunk that needs x_b recomputes it: no barrier, no flag.
+__device__ __forceinline__ void border_solution_partials(double (&xb)[NB], const Geom& g, const Buf& b,
+                                                         int sys, int fwd_tiles, int fwd_tile_rows) {
   const double* Y = b.Y + sys * vstride(g);
   const int glead = b.lead[sys * 2 + 1];
   double acc[NB];
@@ -1297,12 +1320,91 @@ __device__ __forceinline__ void border_solution(double (&xb)[NB], const Geom& g,
   }
 }
 
+// x_b = S^-1 (y_b - G^T y).  G is non-zero only on the leading `lead` rows and the
+// last NB interior rows.  The first tile of the backward sweep (it owns the border)
+// reduces G^T y with the whole CTA in a fixed order and publishes x_b; the few other
+// chunks that need it (top tiles, processed last) read it behind an epoch flag.
+__device__ __forceinline__ void border_solution_cta(double (&xb)[NB], const Geom& g, const Buf& b,
+                                                    const Stage& st, int sys, double (*s_red)[NB],
+                                                    double* s_xb) {
+  const long long vs = vstride(g);
+  const double* Y = b.Y + sys * vs;
+  const double* G = b.Gb + sys * vs * NB;
+  const int glead = b.lead[sys * 2 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  double acc[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) acc[c] = 0.0;
+  const int bot0 = g.nhat - NB;
+  if (st.use_partials) {
+    // the forward sweep left per-tile partial sums: add them in tile order
+    if (threadIdx.x == 0) {
+      const int ft = st.fwd_tiles, fr = st.fwd_tile_rows;
+      const int nlead = (glead + fr - 1) / fr;
+      const int tail0 = bot0 / fr, tail1 = (g.nhat - 1) / fr;
+      for (int t = 0; t < ft; ++t) {
+        if (t < nlead || (t >= tail0 && t <= tail1)) {
+#pragma unroll
+          for (int c = 0; c < NB; ++c) acc[c] += __ldcg(b.gpart + ((long long)sys * ft + t) * NB + c);
+        } else if (t < tail0) {
+          t = tail0 - 1;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NB; ++c) s_red[0][c] = acc[c];
+    }
+  } else
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int lo = pass == 0 ? 0 : (glead > bot0 ? glead : bot0);
+    const int hi = pass == 0 ? (glead < g.nhat ? glead : g.nhat) : g.nhat;
+    for (int r = lo + (int)threadIdx.x; r < hi; r += (int)blockDim.x) {
+      const double yr = Y[ridx(r)];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) acc[c] += G[fidx(r, c, NB)] * yr;
+    }
+  }
+  if (!st.use_partials) {
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], d);
+      if (lane == 0) s_red[warp][c] = acc[c];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double yb[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      double v = 0.0;
+      for (int w = 0; w < (st.use_partials ? 1 : nwarps); ++w) v += s_red[w][c];
+      yb[c] = Y[ridx(g.nhat + c)] - v;
+    }
+    const double* Si = b.Sinv + (long long)sys * NB * NB;
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      double sum = 0.0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) sum += Si[r * NB + c] * yb[c];
+      s_xb[r] = sum;
+      b.xb[(long long)sys * (NB + 1) + r] = sum;
+    }
+    st_flag((int*)(b.xb + (long long)sys * (NB + 1) + NB), g.epoch);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NB; ++c) xb[c] = s_xb[c];
+}
+
 // ---- backward substitution: U x = y - W x_b ; k_i = x - sum cfac_j k_j ;
 //      last stage: U_new = U + sum b_i k_i and the embedded error estimate
 template <int NPREV, int LAST>
 __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stage& st) {
   __shared__ double smem[(MAXW + 1) * KMAX];
   __shared__ double s_err[MAXW];
+  __shared__ double s_bred[MAXW][NB];
+  __shared__ double s_xb[NB];
   __shared__ __align__(8) unsigned long long s_bar;
   extern __shared__ __align__(128) double dsm[];
   int sys, tile;
@@ -1333,6 +1435,16 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
     const double* Yg = b.Y + sys * vs + cb;
 #pragma unroll
     for (int r = 0; r < C; ++r) yreg[r] = Yg[(long long)r * 32];
+    // the second pass reads k_j (and U for the update): start those lines moving now
+#pragma unroll
+    for (int r = 0; r < C; ++r) {
+#pragma unroll
+      for (int q = 0; q < (NPREV < 0 ? MAXS : NPREV); ++q)
+        if (NPREV >= 0 || q < st.nprev)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(b.K[q] + sys * vs + cb + (long long)r * 32));
+      if (LAST != 0)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(b.U + sys * vs + cb + (long long)r * 32));
+    }
   }
   const int r0 = chunk * C;
   const int wlead = b.lead[sys * 2 + 0];
@@ -1343,7 +1455,16 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
   for (int c = 0; c < NB; ++c) xb[c] = 0.0;
   // border coupling of this chunk: y <- y - W x_b on fill rows, border rows <- x_b
   // (applied on the fly in both passes)
-  if (flagged) border_solution(xb, g, b, sys, st.fwd_tiles, st.fwd_tile_rows);
+  if (st.use_partials) {
+    if (flagged) border_solution_partials(xb, g, b, sys, st.fwd_tiles, st.fwd_tile_rows);
+  } else if (tile == 0) {
+    border_solution_cta(xb, g, b, st, sys, s_bred, s_xb);
+  } else if (flagged) {
+    const int* fl = (const int*)(b.xb + (long long)sys * (NB + 1) + NB);
+    while (ld_flag(fl) != g.epoch) {}
+#pragma unroll
+    for (int c = 0; c < NB; ++c) xb[c] = __ldcg(b.xb + (long long)sys * (NB + 1) + c);
+  }
   auto load_y = [&](int r) -> double {
     double yv = yreg[r];
     if (flagged) {

@@ -31,7 +31,7 @@ struct TfBuf {
   double* Gb;           /* border fill row F^T U^-1  [batch][nblk*C*32*NB] */
   double* btab;         /* raw J of border couplings [batch][5][NB][NB] */
   double* Sinv;         /* inverse border Schur complement [batch][NB][NB] */
-  double* xb;           /* border solution           [batch][NB] */
+  double* xb;           /* border solution + epoch flag [batch][NB+1] */
   int* lead;            /* [batch][2] leading rows of W / G that may be non-zero */
   int* status;          /* [batch] bit0: bad pivot, bit1: singular border block */
   double* err;          /* [batch] embedded error estimate of the last step */
@@ -47,6 +47,7 @@ struct TfStage {
   double alpha[TF_MAXS];   /* U_i = U + sum alpha_j k_j */
   double cfac[TF_MAXS];    /* gamma_ij / gamma_ii */
   double dt;
+  int use_partials;        /* border fill known when the fwd sweep runs: fwd leaves partial G^T y */
   int fwd_tiles;           /* tiling of the fwd launch (indexing of gpart) */
   int fwd_tile_rows;
   int is_last;             /* bwd of the last stage: write U_new and the error estimate */

@@ -23,7 +23,8 @@ class Ensemble:
     used; stepping is fixed-step).
     """
 
-    def __init__(self, model, scheme, x, fields, pars, hook=null_hook, batch=None):
+    def __init__(self, model, scheme, x, fields, pars, hook=null_hook, batch=None,
+                 reuse_constant_factor=False):
         self.model, self.scheme = model, scheme
         cm = model._cuda
         x = np.asarray(x, dtype=np.float64)
@@ -45,6 +46,14 @@ class Ensemble:
         if not scheme._on_device(hook):
             raise ValueError("ensembles take declarative hooks (schemes.Dirichlet) only")
         scheme._set_hook(self.state, hook)
+        self.factor_reuse = False
+        if reuse_constant_factor:
+            # legitimate only when J does not depend on the state (SURVEY.md §7
+            # "State-independent J"); the reference refactorises every step anyway
+            if not self.state.variant.lowered.jacobian_is_constant:
+                raise ValueError("reuse_constant_factor needs a state-independent Jacobian")
+            _lib.check(_lib.lib().tf_state_set_factor_reuse(self.state.h, 1))
+            self.factor_reuse = True
         self.t = 0.0
 
     def upload(self, u):
