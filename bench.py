@@ -229,6 +229,31 @@ def run_gpu(args):
     assert not status.any(), "factorisation failed in the bench"
     assert np.isfinite(h_in).all(), "non-finite state after the bench"
 
+    extras = {}
+    if args.workload == "ensemble" and ens.state.variant.lowered.jacobian_is_constant:
+        # same workload with the factorisation kept across steps (legitimate for this
+        # linear model; NOT the headline: the reference refactorises)
+        _lib.check(lib.tf_state_set_factor_reuse(ens.state.h, 1))
+        ens.step(dt, 2)
+        ens.sync()
+        _lib.check(lib.tf_ctx_timer_start(ctx))
+        ens.step(dt, args.steps)
+        ms2 = ctypes.c_float()
+        _lib.check(lib.tf_ctx_timer_stop(ctx, ctypes.byref(ms2)))
+        _lib.check(lib.tf_state_set_factor_reuse(ens.state.h, 0))
+        t2 = D.max_over_ranks(ms2.value * 1e-3)
+        extras["factor_reuse"] = {"value": total_units * args.steps / t2,
+                                  "ms_per_step": t2 * 1e3 / args.steps,
+                                  "note": "factor kept while gamma*dt is constant"}
+    ens.state.close()
+    if rank == 0 and ws == 1 and args.others:
+        for other in ("ks", "burgers", "film"):
+            if other == args.workload:
+                continue
+            try:
+                extras[other] = quick_measure(other, min(args.steps, 10))
+            except Exception as e:  # noqa: BLE001  (never lose the headline line)
+                extras[other] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     cpu = None
     if rank == 0 and ws == 1 and not args.no_cpu:
         cpu = cpu_baseline(args.workload, args.cpu_seconds)
@@ -248,10 +273,37 @@ def run_gpu(args):
                        "working set %.0f MB fits L2; no flush (steps are dependent)" % (
                            units * wk["Q"] / 1e6)},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "other_workloads": extras,
         }
         print(json.dumps(out))
     D.finalize()
+
+
+def quick_measure(workload, steps):
+    """Short device-resident measurement of another BASELINE workload (1 GPU)."""
+    import ctypes
+    from triflow_b200 import _lib
+    from triflow_b200.ensemble import Ensemble
+    from triflow_b200.model import Model
+    wk = WORKLOADS[workload]
+    mname, mk_scheme, x, fields, pars, hook, batch, N, dt = build_problem(workload, None)
+    model = Model(**W.model_args(mname), compiler="cuda")
+    scheme = mk_scheme(model)
+    ens = Ensemble(model, scheme, x, fields, pars, hook=hook, batch=batch)
+    lib, ctx = _lib.lib(), model._cuda.ctx
+    ens.step(dt, 3)
+    ens.sync()
+    _lib.check(lib.tf_ctx_timer_start(ctx))
+    _lib.check(lib.tf_scheme_step(ens.state.h, scheme.handle, float(dt), steps, None))
+    ms = ctypes.c_float()
+    _lib.check(lib.tf_ctx_timer_stop(ctx, ctypes.byref(ms)))
+    peak, _ = peaks()
+    rate = float(N) * batch * steps / (ms.value * 1e-3)
+    assert np.isfinite(ens.download()).all()
+    ens.state.close()
+    return {"config": wk["cfg"], "model": mname, "scheme": wk["scheme"], "nodes": N,
+            "value": rate, "ms_per_step": ms.value / steps,
+            "bytes_per_node_step": wk["Q"], "step_frac": round(wk["Q"] * rate / 1e9 / peak, 4)}
 
 
 # -------------------------------------------------------------- CPU baseline
@@ -357,6 +409,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", dest="others", action="store_false",
+                    help="skip the short ks/burgers/film measurements added to the line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -63,3 +63,5 @@ if __name__ == "__main__":
         for N, nb in ((4096, 256), (3072, 342), (2048, 512), (65536, 16)):
             c = W.kuramoto(N)
             run("ks", c, lambda m: S.ROS3PRw(m, **fx), batch=nb)
+    elif what == "film":
+        run("film", W.film(2 ** 18), lambda m: S.Theta(m, theta=1))
