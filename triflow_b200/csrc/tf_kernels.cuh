@@ -308,20 +308,46 @@ __device__ Mon tile_scan(const Mon& mine, double* smem /* (MAXW+1)*K doubles */,
 }
 
 // Tile / system assignment.  One tile per system: blockIdx.  Otherwise a ticket
-// (monotone counter, the launch's base is passed in), so that every tile a CTA
-// may wait for is already running (look-back forward progress).
-__device__ __forceinline__ void resolve_tile(const Geom& g, const Buf& b, int& sys, int& tile) {
+// (monotone counter), so that every tile a CTA may wait for is already running
+// (look-back forward progress).  The flag epoch and the ticket base of the launch live
+// in device memory (b.ctl) and are advanced by the last CTA of every chained kernel
+// (finish_chain), so kernel parameters do not change from step to step and a whole
+// step can be replayed from a CUDA graph.
+__device__ __forceinline__ void resolve_tile(const Geom& g, const Buf& b, int& sys, int& tile,
+                                             int& epoch) {
   if (g.tiles == 1) {
     sys = blockIdx.x;
     tile = 0;
+    epoch = 0;
     return;
   }
   __shared__ unsigned s_ticket;
-  if (threadIdx.x == 0) s_ticket = atomicAdd((unsigned*)b.flags, 1u) - (unsigned)g.ticket_base;
+  __shared__ int s_epoch;
+  if (threadIdx.x == 0) {
+    s_epoch = *((volatile int*)(b.ctl + 0));
+    const unsigned base = *((volatile unsigned*)(b.ctl + 1));
+    s_ticket = atomicAdd((unsigned*)b.flags, 1u) - base;
+  }
   __syncthreads();
   const int t = (int)s_ticket;
+  epoch = s_epoch;
   sys = t / g.tiles;
   tile = t - sys * g.tiles;
+}
+
+// Last CTA of a chained launch: new epoch and ticket base for the next launch.
+__device__ __forceinline__ void finish_chain(const Geom& g, const Buf& b, int epoch) {
+  if (g.tiles == 1) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x;
+    const unsigned d = atomicAdd((unsigned*)(b.ctl + 2), 1u);
+    if (d == total - 1) {
+      b.ctl[2] = 0;
+      b.ctl[0] = (epoch >= (1 << 28)) ? 1 : epoch + 1;
+      *((unsigned*)(b.ctl + 1)) += total;
+    }
+  }
 }
 
 // ------------------------------------------------------------ stencil windows
@@ -594,8 +620,8 @@ extern "C" __global__ void __launch_bounds__(256) tf_k_eval_J(Geom g, Buf b, dou
 // ---- factor: A = I - a*J(U) -> banded LU (chunk scan with linear-fractional maps)
 __device__ __forceinline__ void factor_body_rows(const Geom& g, const Buf& b, double a) {
   __shared__ double smem[(MAXW + 1) * KMAX];
-  int sys, tile;
-  resolve_tile(g, b, sys, tile);
+  int sys, tile, epoch;
+  resolve_tile(g, b, sys, tile, epoch);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int blk = tile * nwarps + warp;
   const bool active = blk < g.nblk;
@@ -613,7 +639,7 @@ __device__ __forceinline__ void factor_body_rows(const Geom& g, const Buf& b, do
     tfb::ChunkLU<BETA, C>::run1(A, mine, bad);
   }
   const Star pre = tile_scan<Star>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
-                                   g.epoch, Star::identity(), nullptr);
+                                   epoch, Star::identity(), nullptr);
   if (active) {
     double Uf[C][BETA + 1], Lown[C][BETA], Lnext[BETA][BETA];
     tfb::ChunkLU<BETA, C>::run2(A, pre.P(), Uf, Lown, Lnext, bad);
@@ -640,6 +666,7 @@ __device__ __forceinline__ void factor_body_rows(const Geom& g, const Buf& b, do
     }
     if (bad) atomicOr(b.status + sys, 1);
   }
+  finish_chain(g, b, epoch);
 }
 
 // ---- streaming factorisation for scalar models (V == 1: rows == nodes, BETA == P).
@@ -705,8 +732,8 @@ __device__ __forceinline__ void factor_body_stream(const Geom& g, const Buf& b, 
   constexpr int NSB = C / BETA;                   // sub-blocks per chunk
   __shared__ double smem[(MAXW + 1) * KMAX];
   __shared__ double s_cst[NC2];
-  int sys, tile;
-  resolve_tile(g, b, sys, tile);
+  int sys, tile, epoch;
+  resolve_tile(g, b, sys, tile, epoch);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int blk = tile * nwarps + warp;
   const bool active = blk < g.nblk;
@@ -767,7 +794,7 @@ __device__ __forceinline__ void factor_body_stream(const Geom& g, const Buf& b, 
       if (!(fabs(mine.d[q]) < 1e300)) bad = 1;
   }
   const Star pre = tile_scan<Star>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
-                                   g.epoch, Star::identity(), nullptr);
+                                   epoch, Star::identity(), nullptr);
   if (active) {
     double X[BETA * BETA];
 #pragma unroll
@@ -834,6 +861,7 @@ __device__ __forceinline__ void factor_body_stream(const Geom& g, const Buf& b, 
     }
     if (bad) atomicOr(b.status + sys, 1);
   }
+  finish_chain(g, b, epoch);
 }
 
 #ifndef TF_FACTOR_STREAM
@@ -1139,8 +1167,8 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
   __shared__ double s_part[MAXW][NB];
   __shared__ __align__(8) unsigned long long s_bar;
   extern __shared__ __align__(128) double dsm[];
-  int sys, tile;
-  resolve_tile(g, b, sys, tile);
+  int sys, tile, epoch;
+  resolve_tile(g, b, sys, tile, epoch);
   const int T = blockDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
   double* sL = dsm;                        // [T*C*BETA] L rows of the tile (TMA)
@@ -1231,7 +1259,7 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
     rs.to_map(mine);
   }
   const Aff pre = tile_scan<Aff>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
-                                 g.epoch, Aff::identity(), nullptr);
+                                 epoch, Aff::identity(), nullptr);
   // second pass with the true incoming state; when the border fill of this step is
   // already complete (every stage but the first) the tile also reduces its share of G^T y
   const int tile_rows = nwarps * 32 * C;
@@ -1277,6 +1305,7 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
       b.gpart[((long long)sys * g.tiles + tile) * NB + threadIdx.x] = v;
     }
   }
+  finish_chain(g, b, epoch);
 }
 
 #define TF_FWD_KERNEL(name, NP)                                                          \
@@ -1325,8 +1354,8 @@ __device__ __forceinline__ void border_solution_partials(double (&xb)[NB], const
 // reduces G^T y with the whole CTA in a fixed order and publishes x_b; the few other
 // chunks that need it (top tiles, processed last) read it behind an epoch flag.
 __device__ __forceinline__ void border_solution_cta(double (&xb)[NB], const Geom& g, const Buf& b,
-                                                    const Stage& st, int sys, double (*s_red)[NB],
-                                                    double* s_xb) {
+                                                    const Stage& st, int sys, int epoch,
+                                                    double (*s_red)[NB], double* s_xb) {
   const long long vs = vstride(g);
   const double* Y = b.Y + sys * vs;
   const double* G = b.Gb + sys * vs * NB;
@@ -1390,7 +1419,7 @@ __device__ __forceinline__ void border_solution_cta(double (&xb)[NB], const Geom
       s_xb[r] = sum;
       b.xb[(long long)sys * (NB + 1) + r] = sum;
     }
-    st_flag((int*)(b.xb + (long long)sys * (NB + 1) + NB), g.epoch);
+    st_flag((int*)(b.xb + (long long)sys * (NB + 1) + NB), epoch);
   }
   __syncthreads();
 #pragma unroll
@@ -1407,8 +1436,8 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
   __shared__ double s_xb[NB];
   __shared__ __align__(8) unsigned long long s_bar;
   extern __shared__ __align__(128) double dsm[];
-  int sys, tile;
-  resolve_tile(g, b, sys, tile);
+  int sys, tile, epoch;
+  resolve_tile(g, b, sys, tile, epoch);
   const int T = blockDim.x;
   const int lane_l = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
   double* sU = dsm;                               // [T*C*(BETA+1)] U rows of the tile (TMA)
@@ -1458,10 +1487,10 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
   if (st.use_partials) {
     if (flagged) border_solution_partials(xb, g, b, sys, st.fwd_tiles, st.fwd_tile_rows);
   } else if (tile == 0) {
-    border_solution_cta(xb, g, b, st, sys, s_bred, s_xb);
+    border_solution_cta(xb, g, b, st, sys, epoch, s_bred, s_xb);
   } else if (flagged) {
     const int* fl = (const int*)(b.xb + (long long)sys * (NB + 1) + NB);
-    while (ld_flag(fl) != g.epoch) {}
+    while (ld_flag(fl) != epoch) {}
 #pragma unroll
     for (int c = 0; c < NB; ++c) xb[c] = __ldcg(b.xb + (long long)sys * (NB + 1) + c);
   }
@@ -1496,7 +1525,7 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
     rs.to_map(mine);
   }
   const Aff pre = tile_scan<Aff>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
-                                 g.epoch, Aff::identity(), nullptr);
+                                 epoch, Aff::identity(), nullptr);
   double emax = 0.0;
   if (active) {
     double sv[BETA];
@@ -1554,6 +1583,7 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
       atomicMax((unsigned long long*)(b.err + sys), (unsigned long long)__double_as_longlong(emax));
     }
   }
+  finish_chain(g, b, epoch);
 }
 
 #define TF_BWD_KERNEL(name, NP, LS)                                                      \

@@ -12,8 +12,6 @@ struct TfGeom {
   int batch;    /* systems */
   int periodic;
   int nhat;     /* interior unknowns (N - P) * V */
-  int epoch;    /* look-back flag epoch of this launch */
-  unsigned ticket_base; /* value of the ticket counter when this launch starts */
 };
 
 struct TfBuf {
@@ -36,6 +34,7 @@ struct TfBuf {
   int* status;          /* [batch] bit0: bad pivot, bit1: singular border block */
   double* err;          /* [batch] embedded error estimate of the last step */
   int* flags;           /* look-back: [0] ticket counter, then [batch*tiles] flags */
+  int* ctl;             /* device-side launch bookkeeping: [0] epoch, [1] ticket base, [2] CTAs done */
   double* lbagg;        /* [batch*tiles][KMAX] tile aggregates */
   double* lbinc;        /* [batch*tiles][KMAX] inclusive prefixes */
   double* gpart;        /* [batch*fwd_tiles][NB] per-tile partial G^T y of the last fwd */
