@@ -1171,6 +1171,7 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
   resolve_tile(g, b, sys, tile, epoch);
   const int T = blockDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
+  const int glead = st.use_partials ? b.lead[sys * 2 + 1] : 0;    // needed late: load early
   double* sL = dsm;                        // [T*C*BETA] L rows of the tile (TMA)
   double* sS = dsm + (size_t)T * C * BETA; // [T*C]      stage state of the tile (halo sharing),
   double* sF = sS;                         //            reused as right-hand side stash
@@ -1193,21 +1194,24 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
     mbar_expect_tx(&s_bar, bytes);
     bulk_g2s(sL, b.Lf + (sys * vs + (long long)blk0 * C * 32) * BETA, bytes, &s_bar);
   }
-  // own stage state -> registers -> shared (neighbours read their halo from there)
+  // own stage state -> registers -> shared (neighbours read their halo from there);
+  // chunks at a tile / domain edge fetch their whole window from global memory in the
+  // same round trip
   double own[C];
+  double win[NF][M + 2 * P];
+  const bool interior = i0 >= P && i0 + M + P <= g.N && P <= M && NH == 0 &&
+                        chunk > blk0 * 32 && chunk < (blk0 + nact) * 32 - 1;
   if (active) {
     const double* U = b.U + sys * vs;
 #pragma unroll
     for (int r = 0; r < C; ++r) own[r] = stage_value<NPREV>(U, b, sys * vs, cb + (long long)r * 32, &st);
+    if (!interior) load_windows<M, NPREV>(win, i0, g, b, sys, &st);
 #pragma unroll
     for (int r = 0; r < C; ++r) sS[sb + r * 32] = own[r];
   }
   __syncthreads();
   Aff mine = Aff::identity();
-  double win[NF][M + 2 * P];
   if (active) {
-    const bool interior = i0 >= P && i0 + M + P <= g.N && P <= M && NH == 0 &&
-                          chunk > blk0 * 32 && chunk < (blk0 + nact) * 32 - 1;
     if (interior) {
 #pragma unroll
       for (int w = 0; w < M + 2 * P; ++w) {
@@ -1221,8 +1225,6 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
         for (int e = 0; e < V; ++e)
           win[e][w] = (dc == 0) ? own[(m * V + e) < C ? (m * V + e) : 0] : sS[nb + (m * V + e) * 32];
       }
-    } else {
-      load_windows<M, NPREV>(win, i0, g, b, sys, &st);
     }
   }
   __syncthreads();                         // every halo has been read: sS becomes sF
@@ -1263,7 +1265,6 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
   // second pass with the true incoming state; when the border fill of this step is
   // already complete (every stage but the first) the tile also reduces its share of G^T y
   const int tile_rows = nwarps * 32 * C;
-  const int glead = st.use_partials ? b.lead[sys * 2 + 1] : 0;
   const int t0 = tile * tile_rows, t1 = t0 + tile_rows;
   const bool gtile = st.use_partials && (t0 < glead || (t1 > g.nhat - NB && t0 < g.nhat));
   double acc[NB];
