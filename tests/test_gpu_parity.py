@@ -404,3 +404,26 @@ def test_factor_reuse_is_bit_identical_for_constant_jacobian():
         km = gmodel("ks")
         ck = W.kuramoto(1024)
         Ensemble(km, S.ROS2(km), ck["x"], ck["fields"], ck["pars"], reuse_constant_factor=True)
+
+
+# ------------------------------------------- BASELINE.json full sizes vs the oracle
+@pytest.mark.parametrize("which,steps", [("burgers", 10), ("ks", 3), ("film", 2)])
+def test_full_size_configs_vs_oracle(which, steps):
+    """cfg 2 (N=2^17, ROS2), cfg 3 (N=2^20, ROS3PRw), cfg 4 (N=2^18, Theta) at the
+    BASELINE sizes against the CPU oracle (a few steps: the oracle needs seconds
+    per step at these sizes)."""
+    from oracle import schemes as O
+    from triflow_b200 import schemes as S, workloads as W
+    if which == "burgers":
+        c, name, mk = W.burgers(2 ** 17, 1), "burgers_up1", lambda mod, m: mod.ROS2(m)
+    elif which == "ks":
+        c, name, mk = W.kuramoto(2 ** 20), "ks", lambda mod, m: mod.ROS3PRw(m, **FX)
+    else:
+        c, name, mk = W.film(2 ** 18), "film", lambda mod, m: mod.Theta(m, theta=1)
+    gm, om = gmodel(name), omodel(name)
+    f0 = gm.fields_template(x=c["x"], **c["fields"])
+    _, fg = mk(S, gm).run_fixed(0.0, f0, c["dt"], steps, c["pars"])
+    fo, t, sch = om.fields_template(x=c["x"], **c["fields"]), 0.0, mk(O, om)
+    for _ in range(steps):
+        t, fo = sch(t, fo, c["dt"], c["pars"])
+    assert rel_traj_err(fg.uflat, fo.uflat) <= TRAJ_TOL
