@@ -427,3 +427,37 @@ def test_full_size_configs_vs_oracle(which, steps):
     for _ in range(steps):
         t, fo = sch(t, fo, c["dt"], c["pars"])
     assert rel_traj_err(fg.uflat, fo.uflat) <= TRAJ_TOL
+
+
+def test_lazy_fields_keep_the_state_on_the_device():
+    """Opt-in lazy=True: same trajectory as the eager path, no PCIe traffic between
+    untouched outputs, consumed objects fail loudly."""
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.fields import LazyFields
+    from triflow_b200.simulation import Simulation
+    c = W.readme(200)
+    m = gmodel("advdiff")
+    hook = S.Dirichlet(U=(1, 0))
+    runs = []
+    for lazy in (False, True):
+        sim = Simulation(m, dict(x=c["x"], **c["fields"]), c["pars"], dt=c["dt"], tmax=c["tmax"],
+                         hook=hook, scheme=S.ROS3PRw, time_stepping=False, lazy=lazy)
+        outs = [f for _, f in sim]
+        runs.append(outs)
+    assert isinstance(runs[1][-1], LazyFields) and not isinstance(runs[0][-1], LazyFields)
+    assert np.array_equal(runs[0][-1].uflat, runs[1][-1].uflat)
+    assert runs[1][-1]["U"][0] == 1.0
+    with pytest.raises(RuntimeError):
+        runs[1][0].uflat                      # consumed by the following steps
+    # reading an intermediate result before stepping again is fine
+    sch = S.ROS2(gmodel("heat"), lazy=True)
+    x = np.linspace(0, 10, 50, endpoint=False)
+    f = gmodel("heat").fields_template(x=x, T=np.cos(x * 2 * np.pi / 10))
+    pars = dict(k=1, periodic=True)
+    t, f1 = sch(0.0, f, 1.0, pars)
+    snap = f1.uflat.copy()
+    t, f2 = sch(t, f1, 1.0, pars)            # f1 was materialised: uploaded again
+    ref = S.ROS2(gmodel("heat"))
+    t, g1 = ref(0.0, f, 1.0, pars)
+    t, g2 = ref(t, g1, 1.0, pars)
+    assert np.array_equal(snap, g1.uflat) and np.array_equal(f2.uflat, g2.uflat)

@@ -131,3 +131,62 @@ class BaseFields:
 
 def _rebuild(deps, helps, data):
     return BaseFields.factory1D(deps, helps)(**data)
+
+
+class LazyFields:
+    """Result of a device-resident scheme call (opt-in, ``scheme(model, lazy=True)``).
+
+    Behaves like the fields container but downloads the unknowns only when they are
+    first touched.  Passing it back to the scheme that produced it *consumes* it: the
+    device state advances in place and nothing crosses PCIe.  Touching a consumed
+    object raises ``RuntimeError`` (read the values before stepping again, or keep
+    ``lazy=False``, which mirrors the reference exactly)."""
+
+    def __init__(self, template, owner, generation):
+        object.__setattr__(self, "_template", template)      # x / helpers / layout
+        object.__setattr__(self, "_owner", owner)
+        object.__setattr__(self, "_generation", generation)
+        object.__setattr__(self, "_real", None)
+
+    def _load(self):
+        if self._real is None:
+            owner = self._owner
+            if owner._generation != self._generation:
+                raise RuntimeError(
+                    "these lazy fields were consumed by a later device step; read them "
+                    "before stepping again or construct the scheme with lazy=False")
+            real = self._template.copy()
+            real.fill(owner._state.download()[0])
+            object.__setattr__(self, "_real", real)
+        return self._real
+
+    def is_resident(self, owner):
+        """True when the device state of ``owner`` still holds exactly these values."""
+        return (self._real is None and owner is self._owner
+                and owner._generation == self._generation)
+
+    # everything else is the container API, after materialisation
+    def __getitem__(self, key):
+        if key == "x" or key in self._template.helper_functions:
+            return self._template[key]
+        return self._load()[key]
+
+    def __setitem__(self, key, value):
+        self._load()[key] = value
+
+    def __getattr__(self, name):
+        if name in ("dependent_variables", "helper_functions", "size", "keys"):
+            return getattr(self._template, name)
+        return getattr(self._load(), name)
+
+    def __iter__(self):
+        return iter(self._template.keys())
+
+    def __contains__(self, key):
+        return key in self._template
+
+    def copy(self, deep=True):
+        return self._load().copy(deep)
+
+    def __repr__(self):
+        return "<LazyFields %s>" % ("on device" if self._real is None else repr(self._real))

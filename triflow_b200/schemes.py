@@ -32,6 +32,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
+from .fields import LazyFields
 
 # ------------------------------------------------------------------ tableaux
 # Numeric constants of the published methods, spelled as the reference spells
@@ -104,6 +105,8 @@ class Dirichlet:
         self.values = {k: (v[0], v[1]) for k, v in values.items()}
 
     def __call__(self, t, fields, pars):
+        if isinstance(fields, LazyFields) and fields._real is None:
+            return fields, pars      # still on the device: the scheme applies the hook there
         for var, (left, right) in self.values.items():
             if left is not None:
                 fields[var][0] = left
@@ -166,6 +169,8 @@ class _DeviceScheme:
         self._handle = None
         self._state = None
         self._state_key = None
+        self._generation = 0          # bumped whenever the device state changes
+        self.lazy = False             # opt-in: return LazyFields, keep U on the device
 
     @property
     def handle(self):
@@ -193,7 +198,11 @@ class _DeviceScheme:
         st = self._state
         named = {k: fields[k].values for k in self._model._help_funcs}
         st.set_inputs(x, named, pars)
-        st.upload(u=fields.uflat.reshape(1, -1))
+        if not (isinstance(fields, LazyFields) and key == getattr(self, "_resident_key", None)
+                and fields.is_resident(self)):
+            st.upload(u=fields.uflat.reshape(1, -1))
+        self._resident_key = key
+        self._generation += 1         # whatever happens next changes the device state
         return st
 
     def _set_hook(self, st, hook):
@@ -212,6 +221,9 @@ class _DeviceScheme:
             getattr(hook, "__name__", "") == "null_hook"
 
     def _result(self, fields, st):
+        if self.lazy:
+            template = fields._template if isinstance(fields, LazyFields) else fields
+            return LazyFields(template, self, self._generation)
         out = fields.copy()
         out.fill(st.download()[0])
         return out
@@ -234,7 +246,8 @@ class _DeviceScheme:
                 t, fields, _, pars = self._fixed_step_host_hook(t, fields, dt, pars, hook)
                 fields, pars = hook(t, fields, pars)
             return t, fields
-        fields, pars = hook(t, fields.copy(), pars)
+        if not isinstance(fields, LazyFields):
+            fields, pars = hook(t, fields.copy(), pars)
         st = self._bind(fields, pars)
         self._set_hook(st, hook)
         _lib.check(_lib.lib().tf_scheme_step(st.h, self.handle, float(dt), int(n_steps), None))
@@ -267,7 +280,7 @@ class ROW_general(_DeviceScheme):
                 raise ValueError("time_stepping=True needs a tolerance")
             return self._variable_step(t, fields, dt, pars, hook)
         if self._on_device(hook):
-            st = self._bind(fields.copy(), pars)
+            st = self._bind(fields, pars)
             self._set_hook(st, hook)
             err = np.empty(1)
             _lib.check(_lib.lib().tf_scheme_step(st.h, self.handle, float(dt), 1,
@@ -285,7 +298,7 @@ class ROW_general(_DeviceScheme):
             raise NotImplementedError(
                 "recompute_target=False (interpolated output) is not implemented")
         if self._on_device(hook):
-            st = self._bind(fields.copy(), pars)
+            st = self._bind(fields, pars)
             self._set_hook(st, hook)
             idt = C.c_double(-1.0 if self._internal_dt is None else self._internal_dt)
             nfs = C.c_int(0)
@@ -335,20 +348,22 @@ class ROW_general(_DeviceScheme):
 class ROS2(ROW_general):
     """Second order Rosenbrock scheme, fixed step (``schemes.py:241-256``)."""
 
-    def __init__(self, model):
+    def __init__(self, model, lazy=False):
         alpha, gamma, b, _ = tableau("ROS2")
         super().__init__(model, alpha, gamma, b, time_stepping=False)
+        self.lazy = lazy
 
 
 class _Embedded(ROW_general):
     _name = None
 
     def __init__(self, model, tol=1e-1, time_stepping=True, max_iter=None, dt_min=None,
-                 recompute_target=True):
+                 recompute_target=True, lazy=False):
         alpha, gamma, b, b_pred = tableau(self._name)
         super().__init__(model, alpha, gamma, b, b_pred=b_pred,
                          time_stepping=time_stepping, tol=tol, max_iter=max_iter,
                          dt_min=dt_min, recompute_target=recompute_target)
+        self.lazy = lazy
 
 
 class ROS3PRw(_Embedded):
@@ -372,7 +387,7 @@ class Theta(_DeviceScheme):
     Crank-Nicolson.  The pluggable ``solver(A, b)`` of the reference is replaced by
     the device banded solver and cannot be overridden."""
 
-    def __init__(self, model, theta=1, solver=None):
+    def __init__(self, model, theta=1, solver=None, lazy=False):
         if solver is not None:
             raise ValueError("triflow_b200.Theta solves on the device; a custom "
                              "solver(A, b) cannot be plugged in")
@@ -380,10 +395,11 @@ class Theta(_DeviceScheme):
             raise ValueError("theta=0 (explicit Euler) has no implicit system to solve")
         self._theta = theta
         super().__init__(model, np.zeros((1, 1)), np.array([[float(theta)]]), [1.0], None)
+        self.lazy = lazy
 
     def __call__(self, t, fields, dt, pars, hook=null_hook):
         if self._on_device(hook):
-            st = self._bind(fields.copy(), pars)
+            st = self._bind(fields, pars)
             self._set_hook(st, hook)
             _lib.check(_lib.lib().tf_scheme_step(st.h, self.handle, float(dt), 1, None))
             return t + dt, self._result(fields, st)
