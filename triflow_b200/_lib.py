@@ -74,7 +74,7 @@ def build_cubin(header, chunk_nodes, warps, fast_div=False):
     """Compile a generated model header + tf_kernels.cuh to an sm_100a cubin."""
     os.makedirs(CACHE, exist_ok=True)
     digest = _sources_digest([os.path.join(CSRC, s) for s in _KERNEL_SRCS])
-    minb = int(os.environ.get("TF_MINB", "2"))
+    minb = int(os.environ.get("TF_MINB", "0"))          # 0: the kernels' own default
     extra = os.environ.get("TF_CFLAGS", "").split()          # tuning knobs (-DTF_...)
     key = hashlib.sha1(("%s|%s|%d|%d|%d|%s" % (header, digest, chunk_nodes, minb,
                                                int(fast_div), extra)).encode()).hexdigest()[:20]
@@ -88,7 +88,7 @@ def build_cubin(header, chunk_nodes, warps, fast_div=False):
     tmp = cubin + ".tmp%d" % os.getpid()
     cmd = [_nvcc(), *ARCH, "-O3", "-std=c++17", "-lineinfo", "-I", CSRC,
            "-DTF_M=%d" % chunk_nodes, "-DTF_FAST_DIV=%d" % int(fast_div),
-           "-DTF_MINB=%d" % minb, *extra, "-cubin", "-o", tmp, src]
+           *(["-DTF_MINB=%d" % minb] if minb else []), *extra, "-cubin", "-o", tmp, src]
     subprocess.check_call(cmd)
     os.replace(tmp, cubin)
     return cubin

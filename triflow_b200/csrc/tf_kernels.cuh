@@ -32,7 +32,9 @@
 #endif
 #define TF_MAXW 16 /* max warps per CTA (runtime: blockDim.x / 32) */
 #ifndef TF_MINB
-#define TF_MINB 2 /* min CTAs of 512 threads per SM for the sweep kernels (register cap 64) */
+/* min CTAs of 512 threads per SM for the sweep kernels: register cap 64 for narrow bands,
+   128 for wide bands (their recurrence state alone is 60 doubles) */
+#define TF_MINB (((TF_P * TF_NVAR + TF_NVAR - 1) <= 2) ? 2 : 1)
 #endif
 
 namespace tfk {
@@ -124,9 +126,24 @@ __device__ __forceinline__ Mon select(bool c, const Mon& a, const Mon& b) {
   for (int k = 0; k < Mon::K; ++k) o.d[k] = c ? a.d[k] : b.d[k];
   return o;
 }
+// out-of-line combine for wide maps (one copy of the code, one stack frame)
+template <class Mon>
+__device__ __noinline__ Mon combine_call(const Mon& a, const Mon& b) {
+  return Mon::combine(a, b);
+}
+
 // inclusive scan over the lanes of a warp, lower lane = earlier
 template <class Mon>
 __device__ __forceinline__ Mon warp_scan(Mon v, int lane) {
+  if (Mon::K > 1000) {                     // (rolled variant for very wide maps: measured slower at K = 30, 100)
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+      const Mon o = shfl_up(v, d);
+      const Mon c = combine_call(o, v);
+      v = select(lane >= d, c, v);
+    }
+    return v;
+  }
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const Mon o = shfl_up(v, d);
@@ -138,6 +155,15 @@ __device__ __forceinline__ Mon warp_scan(Mon v, int lane) {
 // ordered reduction, HIGHER lane = earlier; result valid in lane 0
 template <class Mon>
 __device__ __forceinline__ Mon warp_reduce_rev(Mon v, int lane) {
+  if (Mon::K > 1000) {
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+      const Mon o = shfl_down(v, d);
+      const Mon c = combine_call(o, v);
+      v = select(lane + d < 32, c, v);
+    }
+    return v;
+  }
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const Mon o = shfl_down(v, d);
