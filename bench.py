@@ -265,7 +265,7 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %s" % (wk["cfg"], args.workload),
-                       "model": mname, "scheme": wk["scheme"], "nodes": N,
+                       "pde": mname, "scheme": wk["scheme"], "nodes": N,
                        "systems_per_gpu": batch, "dt": dt, "fixed_step": True,
                        "parallelism": "members sharded x%d, no collective" % ws,
                        "l2": "working set %.0f MB per GPU > 126 MB L2" % (
@@ -301,7 +301,7 @@ def quick_measure(workload, steps):
     rate = float(N) * batch * steps / (ms.value * 1e-3)
     assert np.isfinite(ens.download()).all()
     ens.state.close()
-    return {"config": wk["cfg"], "model": mname, "scheme": wk["scheme"], "nodes": N,
+    return {"config": wk["cfg"], "pde": mname, "scheme": wk["scheme"], "nodes": N,
             "value": rate, "ms_per_step": ms.value / steps,
             "bytes_per_node_step": wk["Q"], "step_frac": round(wk["Q"] * rate / 1e9 / peak, 4)}
 
