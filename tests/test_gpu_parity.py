@@ -461,3 +461,53 @@ def test_lazy_fields_keep_the_state_on_the_device():
     t, g1 = ref(0.0, f, 1.0, pars)
     t, g2 = ref(t, g1, 1.0, pars)
     assert np.array_equal(snap, g1.uflat) and np.array_equal(f2.uflat, g2.uflat)
+
+
+# ------------------------------------------------ the reference's cookbook models
+COOKBOOK = {
+    # source_doc/source/cookbook/*.rst (examples/notebooks/*.ipynb)
+    "burger_kdv": (("-U * dxU + a * dxxU + b * dxxxU", "U", ["a", "b"]),
+                   dict(a=.03, b=-.02), lambda x: dict(U=np.cos(2 * np.pi * x / x[-1] * 3) + 1.5)),
+    "dropplet": (("dx((h**3 + h**2) * dx(-sigma * dxxh + alpha * (1 / h**3 - e / h**4)))",
+                  "h", ["sigma", "alpha", "e"]),
+                 dict(sigma=1., alpha=.2, e=.1),
+                 lambda x: dict(h=1 + .3 * np.cos(2 * np.pi * x / x[-1] * 2))),
+    "so_wavy": ((["k * dxxU - c * U * dxV", "k * dxxV - c * V * dxU"], ["U", "V"], ["k", "c"]),
+                dict(k=.1, c=1.),
+                lambda x: dict(U=np.cos(2 * np.pi * x / x[-1] * 2), V=np.sin(2 * np.pi * x / x[-1] * 3))),
+    "wave": ((["c**2 * dxxu", "v"], ["v", "u"], "c"), dict(c=2.),
+             lambda x: dict(v=np.zeros_like(x), u=np.exp(-((x - x.mean()) / 3) ** 2))),
+}
+
+
+@pytest.mark.parametrize("name", sorted(COOKBOOK))
+@pytest.mark.parametrize("periodic", [True, False])
+def test_cookbook_models_vs_oracle(name, periodic):
+    """Every PDE of the reference's cookbook: F, J and a few implicit steps."""
+    from oracle import schemes as O
+    from oracle.numpy_compiler import numpy_compiler
+    from triflow_b200 import schemes as S
+    from triflow_b200.model import Model
+    (eqs, deps, pars_names), pvals, ic = COOKBOOK[name]
+    gm = Model(eqs, deps, pars_names, compiler="cuda")
+    om = Model(eqs, deps, pars_names, compiler=numpy_compiler)
+    N = 1500
+    x = np.linspace(0, 40, N, endpoint=False)
+    fields = ic(x)
+    pars = dict(pvals, periodic=periodic)
+    f0 = gm.fields_template(x=x, **fields)
+    # the droplet stencil raises h to the powers 3, 4, -3, -4 (libm pow in the reference,
+    # double-double products here: a few results differ by one ulp) and its expanded form
+    # cancels ~7 digits (terms ~1e8 against |F| ~ 80), so one ulp shows up at 2e-10
+    ftol = 1e-9 if name == "dropplet" else 1e-12
+    F, Fo = gm.F(f0, pars), om.F(f0, pars)
+    assert np.max(np.abs(F - Fo)) <= ftol * max(np.max(np.abs(Fo)), 1e-300)
+    J, Jo = gm.J(f0, pars), om.J(f0, pars)
+    assert abs(J - Jo).max() <= ftol * abs(Jo).max()
+    dt = 1e-3 if name == "dropplet" else 1e-2
+    c = dict(x=x, fields=fields, pars=pars, dt=dt)
+    sg = run_fixed(gm, S.ROS3PRw(gm, **FX), c, 4, 4)
+    fo, t, sch = om.fields_template(x=x, **fields), 0.0, O.ROS3PRw(om, **FX)
+    for _ in range(4):
+        t, fo = sch(t, fo, dt, pars)
+    assert rel_traj_err(sg[-1], fo.uflat) <= TRAJ_TOL

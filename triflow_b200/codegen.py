@@ -208,6 +208,8 @@ class _Lowering:
                 return self._tmp("TF_DIV(1.0, %s)" % base)
             if e == 0.5:
                 return self._tmp("TF_SQRT(%s)" % base)
+            if e == int(e) and 3 <= abs(e) <= 16:
+                return self._tmp("tf_powi(%s, %d)" % (base, int(e)))
             return self._tmp("TF_POW(%s, %s)" % (base, _c_literal(e)))
         return self._tmp("TF_POW(%s, %s)" % (base, self.emit(node.right)))
 

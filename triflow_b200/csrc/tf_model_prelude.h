@@ -37,6 +37,25 @@
 #define TF_FMA(a, b, c) fma((a), (b), (c))
 #endif
 #define TF_POW(a, b) pow((a), (b))
+// x**n for a small literal integer n, evaluated in double-double so that the result is
+// (almost always) the correctly rounded power, like glibc's pow which NumPy calls for
+// array**n (n not in {-1, 0, 0.5, 1, 2}).  CUDA's pow is only accurate to 2 ulp, and the
+// expanded stencils amplify one ulp of a large term by many orders of magnitude.
+TF_HD TF_INLINE double tf_powi(double x, int n) {
+  const int m = n < 0 ? -n : n;
+  double hi = x, lo = 0.0;                       // running power as hi + lo
+  for (int k = 1; k < m; ++k) {
+    const double p = hi * x;
+    const double e = TF_FMA(hi, x, -p) + lo * x; // exact product error + carried low part
+    const double s = p + e;
+    lo = e - (s - p);
+    hi = s;
+  }
+  if (n >= 0) return hi + lo;
+  const double q0 = 1.0 / hi;
+  const double r = TF_FMA(-hi, q0, 1.0) - lo * q0;   // 1 - (hi + lo) * q0
+  return TF_FMA(q0, r, q0);
+}
 #define TF_NAN (__builtin_nan(""))
 #define TF_INF (__builtin_inf())
 
