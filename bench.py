@@ -275,7 +275,7 @@ def run_gpu(args):
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "other_workloads": extras,
         }
-        print(json.dumps(out))
+        _emit(out)
     D.finalize()
 
 
@@ -384,7 +384,7 @@ def run_reference(args):
         v, sample = cpu_rate(args.workload, budget, cores)
         vals.append(v)
     v = float(np.mean(vals))
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": "implicit grid-point*steps/s", "value": v,
         "unit": "grid-point*steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
@@ -393,7 +393,10 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "grid-point*steps/s", "cores": cores,
                          "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "grid-point*steps/s", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 0}}))
+                "d2h_bytes_per_step": 0}})
+
+
+_emit = None
 
 
 def main():
@@ -413,10 +416,25 @@ def main():
                     help="skip the short ks/burgers/film measurements added to the line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly one JSON line: anything a library prints meanwhile (NCCL's
+    # version banner, ...) is routed to stderr, and stdout is restored for the result
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+
+    def _emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)
+    sys.stdout.flush()
+    os.dup2(saved, 1)
 
 
 if __name__ == "__main__":
