@@ -43,7 +43,7 @@ typedef struct {
   int n_nodepar;   /* parameters passed as per-node arrays          */
   int uses_x;      /* expressions reference the coordinate x        */
   int chunk_nodes; /* nodes per thread the cubin was built for      */
-  int warps;       /* warps per CTA the cubin was built for         */
+  int warps;       /* unused (warps per CTA are chosen at launch)   */
 } tf_model_desc;
 
 const char* tf_last_error(void);
@@ -115,6 +115,15 @@ int tf_scheme_step(tf_state_t st, tf_scheme_t sc, double dt, int n_steps, double
 int tf_scheme_advance(tf_state_t st, tf_scheme_t sc, double t, double dt, double tol,
                       double safety_factor, int max_iter, double dt_min, int recompute_target,
                       double* internal_dt, int* n_fixed_steps, double* last_err);
+
+/* ROW_general._variable_step (core/schemes.py:176-238) run independently for every member
+ * of an ensemble (each system keeps its own internal step size; systems must fit one CTA
+ * tile, i.e. n_nodes <= 16*32*chunk_nodes).  All arrays have `batch` entries.
+ *   internal_dt  in/out, < 0 means "None";  n_fixed_steps, fail (0 or TF_EMAXITER /
+ *   TF_EDTMIN per member) out.  Returns TF_EMAXITER / TF_EDTMIN if any member failed. */
+int tf_ensemble_advance(tf_state_t st, tf_scheme_t sc, double t, double dt, double tol,
+                        double safety_factor, int max_iter, double dt_min, double* internal_dt,
+                        int* n_fixed_steps, int* fail);
 
 /* Optional: keep the factorisation across steps while gamma*dt is unchanged.  Only valid
  * for models whose Jacobian does not depend on the state (linear models with uniform

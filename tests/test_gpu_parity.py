@@ -511,3 +511,34 @@ def test_cookbook_models_vs_oracle(name, periodic):
     for _ in range(4):
         t, fo = sch(t, fo, dt, pars)
     assert rel_traj_err(sg[-1], fo.uflat) <= TRAJ_TOL
+
+
+def test_ensemble_per_member_adaptive_controller():
+    """Every member runs its own _variable_step controller on the device: same internal
+    step counts and trajectories as independent oracle runs (reference schemes.py:176-238)."""
+    from oracle import schemes as O
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.ensemble import Ensemble
+    mem = np.array([0, 127, 9000, 16384, 32767])
+    c = W.ensemble(200, mem)
+    gm, om = gmodel("advdiff"), omodel("advdiff")
+    ens = Ensemble(gm, S.ROS3PRw(gm, tol=1e-1), c["x"], c["fields"], c["pars"],
+                   hook=S.Dirichlet(U=(1.0, 0.0)), batch=len(mem))
+    counts = [ens.advance(0.5).copy() for _ in range(3)]
+    U = ens.download()
+    for idx in range(len(mem)):
+        pars = dict(k=float(c["pars"]["k"][idx]), c=float(c["pars"]["c"][idx]), periodic=False)
+        sch = O.ROS3PRw(om, tol=1e-1)
+        f, t, ref_counts = om.fields_template(x=c["x"], **c["fields"]), 0.0, []
+        for _ in range(3):
+            n0 = sch.n_fixed_steps
+            t, f = sch(t, f, 0.5, pars, hook=W.readme_hook)
+            ref_counts.append(sch.n_fixed_steps - n0)
+        assert [int(cn[idx]) for cn in counts] == ref_counts
+        assert rel_traj_err(U[idx], f.uflat) <= TRAJ_TOL
+    # failure modes are reported per member (reference schemes.py:229-238)
+    ens2 = Ensemble(gm, S.ROS3PRw(gm, tol=1e-1, max_iter=2), c["x"], c["fields"], c["pars"],
+                    hook=S.Dirichlet(U=(1.0, 0.0)), batch=len(mem))
+    with pytest.raises(RuntimeError):
+        ens2.advance(0.5)
+    assert (ens2.failed == 3).all()

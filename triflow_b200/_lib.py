@@ -119,6 +119,7 @@ def lib():
         "tf_scheme_step": [vp, vp, d, i, dp],
         "tf_scheme_advance": [vp, vp, d, d, d, d, i, d, i, dp, C.POINTER(i), dp],
         "tf_state_status": [vp, C.POINTER(i)], "tf_state_set_factor_reuse": [vp, i],
+        "tf_ensemble_advance": [vp, vp, d, d, d, d, i, d, dp, C.POINTER(i), C.POINTER(i)],
         "tf_ctx_timer_start": [vp], "tf_ctx_timer_stop": [vp, C.POINTER(C.c_float)],
         "tf_ctx_profile": [vp, i],
         "tf_ctx_profile_read": [vp, i, C.POINTER(C.c_float), C.POINTER(C.c_longlong)],
@@ -138,7 +139,7 @@ EXPORTS = ["tf_last_error", "tf_ctx_create", "tf_ctx_destroy", "tf_ctx_sync", "t
            "tf_state_destroy", "tf_state_upload", "tf_state_download", "tf_eval_F",
            "tf_eval_J", "tf_scheme_create", "tf_scheme_destroy", "tf_hook_set_dirichlet",
            "tf_hook_clear", "tf_scheme_step", "tf_scheme_advance", "tf_state_status",
-           "tf_state_set_factor_reuse",
+           "tf_state_set_factor_reuse", "tf_ensemble_advance",
            "tf_ctx_launch_count", "tf_ctx_timer_start", "tf_ctx_timer_stop",
            "tf_ctx_profile", "tf_ctx_profile_read"]
 

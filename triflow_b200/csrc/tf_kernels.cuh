@@ -644,10 +644,12 @@ extern "C" __global__ void __launch_bounds__(256) tf_k_eval_J(Geom g, Buf b, dou
 }
 
 // ---- factor: A = I - a*J(U) -> banded LU (chunk scan with linear-fractional maps)
-__device__ __forceinline__ void factor_body_rows(const Geom& g, const Buf& b, double a) {
+__device__ __forceinline__ void factor_body_rows(const Geom& g, const Buf& b, double a_uniform) {
   __shared__ double smem[(MAXW + 1) * KMAX];
   int sys, tile, epoch;
   resolve_tile(g, b, sys, tile, epoch);
+  if (b.active != nullptr && !b.active[sys]) return;       // finished ensemble member
+  const double a = (b.asys != nullptr) ? b.asys[sys] : a_uniform;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int blk = tile * nwarps + warp;
   const bool active = blk < g.nblk;
@@ -752,7 +754,7 @@ __device__ __forceinline__ void node_row(double (&row)[WB], const double (&win)[
   }
 }
 
-__device__ __forceinline__ void factor_body_stream(const Geom& g, const Buf& b, double a) {
+__device__ __forceinline__ void factor_body_stream(const Geom& g, const Buf& b, double a_uniform) {
   static_assert(V == 1 || true, "");
   constexpr int NODES = M + EX;
   constexpr int NSB = C / BETA;                   // sub-blocks per chunk
@@ -760,6 +762,8 @@ __device__ __forceinline__ void factor_body_stream(const Geom& g, const Buf& b, 
   __shared__ double s_cst[NC2];
   int sys, tile, epoch;
   resolve_tile(g, b, sys, tile, epoch);
+  if (b.active != nullptr && !b.active[sys]) return;       // finished ensemble member
+  const double a = (b.asys != nullptr) ? b.asys[sys] : a_uniform;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int blk = tile * nwarps + warp;
   const bool active = blk < g.nblk;
@@ -915,11 +919,13 @@ __device__ __forceinline__ long long fidx(int R, int q, int width) {
   return (((long long)(chunk >> 5) * C + j) * width + q) * 32 + (chunk & 31);
 }
 
-extern "C" __global__ void __launch_bounds__(NT) tf_k_border_fill(Geom g, Buf b, double a) {
+extern "C" __global__ void __launch_bounds__(NT) tf_k_border_fill(Geom g, Buf b, double a_uniform) {
   __shared__ double smem[(MAXW + 1) * KMAX];
   __shared__ double s_red[MAXW][NB * NB];
   __shared__ int s_alive;
   const int sys = blockIdx.x;
+  if (b.active != nullptr && !b.active[sys]) return;
+  const double a = (b.asys != nullptr) ? b.asys[sys] : a_uniform;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const long long vs = vstride(g);
   const double* bt = b.btab + (long long)sys * 5 * NB * NB;
@@ -1195,6 +1201,8 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
   extern __shared__ __align__(128) double dsm[];
   int sys, tile, epoch;
   resolve_tile(g, b, sys, tile, epoch);
+  if (b.active != nullptr && !b.active[sys]) return;       // finished ensemble member
+  const double dt = (b.dtsys != nullptr) ? b.dtsys[sys] : st.dt;
   const int T = blockDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
   const int glead = st.use_partials ? b.lead[sys * 2 + 1] : 0;    // needed late: load early
@@ -1272,7 +1280,7 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
 #pragma unroll
       for (int e = 0; e < V; ++e) {
         const int r = m * V + e;
-        double rhs = st.dt * fe[e];
+        double rhs = dt * fe[e];
 #pragma unroll
         for (int q = 0; q < (NPREV < 0 ? MAXS : NPREV); ++q)
           if (NPREV >= 0 || q < st.nprev) rhs += st.cfac[q] * b.K[q][sys * vs + cb + (long long)r * 32];
@@ -1465,6 +1473,7 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
   extern __shared__ __align__(128) double dsm[];
   int sys, tile, epoch;
   resolve_tile(g, b, sys, tile, epoch);
+  if (b.active != nullptr && !b.active[sys]) return;       // finished ensemble member
   const int T = blockDim.x;
   const int lane_l = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
   double* sU = dsm;                               // [T*C*(BETA+1)] U rows of the tile (TMA)
@@ -1635,4 +1644,93 @@ extern "C" __global__ void tf_k_dirichlet(Geom g, double* __restrict__ U, const 
     if (mask & (1 << (2 * e))) u[vidx(0, e)] = dir[2 * e];
     if (mask & (1 << (2 * e + 1))) u[vidx(g.N - 1, e)] = dir[2 * e + 1];
   }
+}
+
+// ---- per-member step-size control of an ensemble: ROW_general._variable_step
+// (reference core/schemes.py:176-238) run independently for every system.
+struct TfCtl {            // one per system
+  double t, next, dt_int, dt_try;
+  int phase;              // 0: attempting, 1: final exact step to the target, 2: done
+  int iters, nfs, fail;   // fail: 3 = max_iter, 4 = dt_min (TF_E* codes)
+};
+
+extern "C" __global__ void tf_k_ctl_init(int batch, TfCtl* c, double* dtsys, double* asys, int* act,
+                                         const double* internal_dt, double t0, double dt_out,
+                                         double gamma) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= batch) return;
+  double d = internal_dt[s] < 0.0 ? 1e-6 : internal_dt[s];
+  d = d < dt_out ? d : dt_out;
+  c[s].t = t0;
+  c[s].next = t0 + dt_out;
+  c[s].dt_int = d;
+  c[s].dt_try = d;
+  c[s].phase = 0;
+  c[s].iters = 0;
+  c[s].nfs = 0;
+  c[s].fail = 0;
+  dtsys[s] = d;
+  asys[s] = gamma * d;
+  act[s] = 1;
+}
+
+// after one attempt of every active member: accept / reject, next dt, commit flags
+extern "C" __global__ void tf_k_ctl_update(int batch, TfCtl* c, double* dtsys, double* asys, int* act,
+                                           int* commit, const double* err, int* n_active,
+                                           double tol, double safety, int max_iter, double dt_min,
+                                           double gamma) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= batch) return;
+  commit[s] = 0;
+  if (!act[s]) return;
+  TfCtl k = c[s];
+  const double e = err[s];
+  k.nfs += 1;
+  if (k.phase == 1) {                       // the exact step to the target is always taken
+    commit[s] = 1;
+    k.t = k.next;
+    k.phase = 2;
+    act[s] = 0;
+  } else {
+    const double new_t = k.t + k.dt_try;
+    k.dt_int = safety * k.dt_try * sqrt(tol / e);
+    if (e > tol) {                          // rejected: same state, smaller step
+      k.dt_try = k.dt_int;
+    } else if (new_t >= k.next) {           // passes the output time: redo with the exact dt
+      k.phase = 1;
+      k.dt_try = k.next - k.t;
+    } else {                                // accepted internal step
+      commit[s] = 1;
+      k.t = new_t;
+      k.iters += 1;
+      k.dt_try = k.dt_int;
+      if (max_iter > 0 && k.iters > max_iter) { k.fail = 3; k.phase = 2; act[s] = 0; }
+      else if (dt_min > 0.0 && k.dt_int < dt_min) { k.fail = 4; k.phase = 2; act[s] = 0; }
+    }
+  }
+  dtsys[s] = k.dt_try;
+  asys[s] = gamma * k.dt_try;
+  c[s] = k;
+  if (act[s]) atomicAdd(n_active, 1);
+}
+
+// U <- U_new for the members whose attempt was accepted
+extern "C" __global__ void tf_k_commit(Geom g, double* __restrict__ U, const double* __restrict__ Un,
+                                       const int* __restrict__ commit) {
+  const int sys = blockIdx.y;
+  if (!commit[sys]) return;
+  const long long vs = vstride(g);
+  for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < vs;
+       a += (long long)gridDim.x * blockDim.x)
+    U[sys * vs + a] = Un[sys * vs + a];
+}
+
+extern "C" __global__ void tf_k_ctl_read(int batch, const TfCtl* c, double* internal_dt, int* nfs,
+                                         int* fail, double* t) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= batch) return;
+  internal_dt[s] = c[s].dt_int;
+  nfs[s] = c[s].nfs;
+  fail[s] = c[s].fail;
+  t[s] = c[s].t;
 }

@@ -67,6 +67,34 @@ class Ensemble:
         self.t += n_steps * dt
         return err
 
+    def advance(self, dt, tol=None, safety_factor=None, max_iter=None, dt_min=None):
+        """Advance every member to ``t + dt`` with its own embedded-error step-size
+        controller (reference ``ROW_general._variable_step``, ``core/schemes.py:176-238``,
+        run per member on the device).  Defaults come from the scheme instance.
+        Returns the number of internal ``_fixed_step`` evaluations per member."""
+        import ctypes as C
+        sch = self.scheme
+        if getattr(sch, "_b_pred", None) is None:
+            raise NotImplementedError("time stepping needs the b predictor coefficients")
+        tol = sch._tol if tol is None else tol
+        if tol is None:
+            raise ValueError("adaptive stepping needs a tolerance")
+        safety = sch._safety_factor if safety_factor is None else safety_factor
+        max_iter = sch._max_iter if max_iter is None else max_iter
+        dt_min = sch._dt_min if dt_min is None else dt_min
+        if not hasattr(self, "_internal_dt"):
+            self._internal_dt = np.full(self.batch, -1.0)
+        nfs = (C.c_int * self.batch)()
+        fail = (C.c_int * self.batch)()
+        rc = _lib.lib().tf_ensemble_advance(
+            self.state.h, sch.handle, float(self.t), float(dt), float(tol), float(safety),
+            int(max_iter or 0), float(dt_min or 0.0), _lib.dptr(self._internal_dt), nfs, fail)
+        self.n_fixed_steps = np.array(nfs[:])
+        self.failed = np.array(fail[:])
+        _lib.check(rc)
+        self.t += dt
+        return self.n_fixed_steps
+
     def download(self, out=None):
         return self.state.download(out)
 
