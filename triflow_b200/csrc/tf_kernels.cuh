@@ -1299,8 +1299,10 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
   // second pass with the true incoming state; when the border fill of this step is
   // already complete (every stage but the first) the tile also reduces its share of G^T y
   const int tile_rows = nwarps * 32 * C;
-  const int t0 = tile * tile_rows, t1 = t0 + tile_rows;
-  const bool gtile = st.use_partials && (t0 < glead || (t1 > g.nhat - NB && t0 < g.nhat));
+  const int t0 = tile * tile_rows;
+  // (the last NB interior rows are added by the backward sweep itself: non-periodic
+  //  systems then skip this reduction altogether)
+  const bool gtile = st.use_partials && t0 < glead;
   double acc[NB];
 #pragma unroll
   for (int c = 0; c < NB; ++c) acc[c] = 0.0;
@@ -1320,7 +1322,7 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
       for (int q = BETA - 1; q > 0; --q) sv[q] = sv[q - 1];
       sv[0] = v;
       Y[(long long)r * 32] = v;
-      if (gtile && fill_row(r0 + r, glead, g)) {
+      if (gtile && r0 + r < glead && r0 + r < g.nhat - NB) {
 #pragma unroll
         for (int c = 0; c < NB; ++c) acc[c] += G[((long long)r * NB + c) * 32] * v;
       }
@@ -1362,13 +1364,16 @@ __device__ __forceinline__ void border_solution_partials(double (&xb)[NB], const
 #pragma unroll
   for (int c = 0; c < NB; ++c) acc[c] = 0.0;
   const int nlead = (glead + fwd_tile_rows - 1) / fwd_tile_rows;
-  const int tail0 = (g.nhat - NB) / fwd_tile_rows, tail1 = (g.nhat - 1) / fwd_tile_rows;
-  for (int t = 0; t < fwd_tiles; ++t) {
-    if (t < nlead || (t >= tail0 && t <= tail1)) {
+  for (int t = 0; t < nlead && t < fwd_tiles; ++t) {
 #pragma unroll
-      for (int c = 0; c < NB; ++c) acc[c] += __ldcg(b.gpart + ((long long)sys * fwd_tiles + t) * NB + c);
-    } else if (t >= nlead && t < tail0) {
-      t = tail0 - 1;                     // skip the untouched middle
+    for (int c = 0; c < NB; ++c) acc[c] += __ldcg(b.gpart + ((long long)sys * fwd_tiles + t) * NB + c);
+  }
+  {
+    const double* G = b.Gb + sys * vstride(g) * NB;
+    for (int r = g.nhat - NB; r < g.nhat; ++r) {       // natural coupling of the last rows
+      const double yr = Y[ridx(r)];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) acc[c] += G[fidx(r, c, NB)] * yr;
     }
   }
   double yb[NB];
@@ -1405,14 +1410,14 @@ __device__ __forceinline__ void border_solution_cta(double (&xb)[NB], const Geom
     if (threadIdx.x == 0) {
       const int ft = st.fwd_tiles, fr = st.fwd_tile_rows;
       const int nlead = (glead + fr - 1) / fr;
-      const int tail0 = bot0 / fr, tail1 = (g.nhat - 1) / fr;
-      for (int t = 0; t < ft; ++t) {
-        if (t < nlead || (t >= tail0 && t <= tail1)) {
+      for (int t = 0; t < nlead && t < ft; ++t) {
 #pragma unroll
-          for (int c = 0; c < NB; ++c) acc[c] += __ldcg(b.gpart + ((long long)sys * ft + t) * NB + c);
-        } else if (t < tail0) {
-          t = tail0 - 1;
-        }
+        for (int c = 0; c < NB; ++c) acc[c] += __ldcg(b.gpart + ((long long)sys * ft + t) * NB + c);
+      }
+      for (int r = bot0; r < g.nhat; ++r) {
+        const double yr = Y[ridx(r)];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) acc[c] += G[fidx(r, c, NB)] * yr;
       }
 #pragma unroll
       for (int c = 0; c < NB; ++c) s_red[0][c] = acc[c];
