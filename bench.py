@@ -208,23 +208,31 @@ def run_gpu(args):
                 "bytes_per_node_step": wk["Q"],
                 "family_ms_per_step": {k: round(v[0] / psteps, 4) for k, v in fam.items()}}
 
-    # -- end to end through the public API with host buffers (upload + step + download)
+    # -- end to end through the public API with HOST buffers: every step uploads the
+    #    unknowns from pinned memory, steps, and downloads the result (the reference's
+    #    scheme(t, fields, dt, pars) convention); member blocks are pipelined over streams
+    from triflow_b200.ensemble import HostPipeline
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     nv = model._nvar
     h_in = _lib.pinned_empty((batch, N * nv))
     h_out = _lib.pinned_empty((batch, N * nv))
     h_in[:] = ens.download()
+    u_before = h_in[0].copy()
+    pipe = HostPipeline(model, scheme, x, fields, pars, hook=hook, batch=batch,
+                        groups=args.e2e_groups)
+    pipe.step_host(h_in, h_out, dt)             # untimed warm-up (result discarded)
     D.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ens.upload(h_in)
-        ens.step(dt, 1)
-        ens.download(h_out)
+        pipe.step_host(h_in, h_out, dt)
         h_in, h_out = h_out, h_in
     t_e2e = D.max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": total_units * e2e_steps / t_e2e, "unit": "grid-point*steps/s",
            "h2d_bytes_per_step": int(8 * N * nv * batch), "d2h_bytes_per_step": int(8 * N * nv * batch),
-           "steps": e2e_steps}
+           "steps": e2e_steps, "ms_per_step": t_e2e * 1e3 / e2e_steps,
+           "api": "HostPipeline.step_host (%d member blocks on their own streams)" % len(pipe.parts)}
+    assert not np.array_equal(u_before, h_in[0]), "the end-to-end pass did not advance the state"
+    pipe.close()
     status = ens.state.status()
     assert not status.any(), "factorisation failed in the bench"
     assert np.isfinite(h_in).all(), "non-finite state after the bench"
@@ -410,6 +418,8 @@ def main():
                     help="ensemble members per GPU")
     ap.add_argument("--nodes", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-groups", type=int, default=16,
+                    help="member blocks of the pipelined host path")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", dest="others", action="store_false",

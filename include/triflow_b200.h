@@ -53,6 +53,15 @@ int tf_ctx_create(int device, tf_ctx_t* out);
 int tf_ctx_destroy(tf_ctx_t ctx);
 int tf_ctx_sync(tf_ctx_t ctx);
 
+/* Asynchronous host-buffer mode (off by default).  When enabled, tf_state_upload,
+ * tf_state_download and tf_scheme_step enqueue their work on the context's stream and
+ * return without waiting: host buffers must be pinned (tf_host_alloc) and must not be
+ * touched until tf_ctx_sync; failures of the factorisation are then reported by
+ * tf_state_status instead of the return code.  Several contexts on one device overlap
+ * the copies of one group of systems with the stepping of another (the reference copies
+ * nothing: its fields live in host memory, core/fields.py:146-183). */
+int tf_ctx_set_async(tf_ctx_t ctx, int enable);
+
 /* pinned host memory for upload / download buffers */
 int tf_host_alloc(size_t nbytes, void** out);
 int tf_host_free(void* p);

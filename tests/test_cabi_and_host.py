@@ -109,3 +109,16 @@ if rank == 0:
                          env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GATHER_OK" in out.stdout
+
+
+def test_host_pipeline_member_slicing():
+    """HostPipeline splits fields / parameters along the member axis only."""
+    from triflow_b200.ensemble import _members
+    batch, N = 6, 10
+    per_member = np.arange(batch, dtype=float)
+    per_node = np.arange(N, dtype=float)
+    full = np.arange(batch * N, dtype=float).reshape(batch, N)
+    assert np.array_equal(_members(per_member, 2, 5, batch, N), per_member[2:5])
+    assert _members(per_node, 2, 5, batch, N) is per_node
+    assert np.array_equal(_members(full, 2, 5, batch, N), full[2:5])
+    assert _members(0.25, 2, 5, batch, N) == 0.25

@@ -542,3 +542,48 @@ def test_ensemble_per_member_adaptive_controller():
     with pytest.raises(RuntimeError):
         ens2.advance(0.5)
     assert (ens2.failed == 3).all()
+
+
+def test_host_pipeline_equals_blocking_ensemble():
+    """upload -> step -> download pipelined over member blocks (asynchronous contexts)
+    gives bit-identical results to the blocking Ensemble calls, for uneven blocks too."""
+    from triflow_b200 import _lib, schemes as S, workloads as W
+    from triflow_b200.ensemble import Ensemble, HostPipeline
+    mem = np.arange(0, 32768, 1500)                       # 22 members
+    c = W.ensemble(1024, mem)
+    m = gmodel("advdiff")
+    hook = S.Dirichlet(U=(1.0, 0.0))
+    ens = Ensemble(m, S.ROS3PRw(m, **FX), c["x"], c["fields"], c["pars"], hook=hook,
+                   batch=len(mem))
+    u0 = ens.download()
+    rng = np.random.default_rng(3)
+    u0 = u0 + 1e-3 * rng.standard_normal(u0.shape)        # members differ in state as well
+    ens.upload(u0)
+    ens.step(c["dt"], 2)
+    ref = ens.download()
+    pipe = HostPipeline(m, S.ROS3PRw(m, **FX), c["x"], c["fields"], c["pars"], hook=hook,
+                        batch=len(mem), groups=5)
+    assert [hi - lo for lo, hi in pipe.ranges] == [4, 4, 5, 4, 5]
+    h_in = _lib.pinned_empty(u0.shape)
+    h_out = _lib.pinned_empty(u0.shape)
+    h_in[:] = u0
+    pipe.step_host(h_in, h_out, c["dt"], 1)
+    pipe.step_host(h_out, h_in, c["dt"], 1)
+    assert np.array_equal(h_in, ref)
+    assert pipe.launch_count() > 0
+    pipe.close()
+    # a failing factorisation (state-dependent Jacobian, non-finite state) is reported at
+    # the sync point of the asynchronous contexts
+    cb = W.burgers(1024, 1)
+    mb = gmodel("burgers_up1")
+    fields = {"U": np.stack([cb["fields"]["U"]] * 3)}
+    pipe = HostPipeline(mb, S.ROS2(mb), cb["x"], fields, cb["pars"], batch=3, groups=2)
+    h_in = _lib.pinned_empty((3, 1024))
+    h_out = _lib.pinned_empty((3, 1024))
+    h_in[:] = fields["U"]
+    pipe.step_host(h_in, h_out, cb["dt"], 1)
+    assert np.isfinite(h_out).all() and np.array_equal(h_out[0], h_out[2])
+    h_in[1, 10] = np.nan
+    with pytest.raises(RuntimeError):
+        pipe.step_host(h_in, h_out, cb["dt"], 1)
+    pipe.close()

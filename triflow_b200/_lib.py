@@ -107,6 +107,7 @@ def lib():
     L.tf_last_error.restype = C.c_char_p
     sig = {
         "tf_ctx_create": [i, C.POINTER(vp)], "tf_ctx_destroy": [vp], "tf_ctx_sync": [vp],
+        "tf_ctx_set_async": [vp, i],
         "tf_host_alloc": [C.c_size_t, C.POINTER(vp)], "tf_host_free": [vp],
         "tf_model_load": [vp, vp, C.c_size_t, C.POINTER(ModelDesc), C.POINTER(vp)],
         "tf_model_unload": [vp],
@@ -134,7 +135,8 @@ def lib():
     return L
 
 
-EXPORTS = ["tf_last_error", "tf_ctx_create", "tf_ctx_destroy", "tf_ctx_sync", "tf_host_alloc",
+EXPORTS = ["tf_last_error", "tf_ctx_create", "tf_ctx_destroy", "tf_ctx_sync", "tf_ctx_set_async",
+           "tf_host_alloc",
            "tf_host_free", "tf_model_load", "tf_model_unload", "tf_state_create",
            "tf_state_destroy", "tf_state_upload", "tf_state_download", "tf_eval_F",
            "tf_eval_J", "tf_scheme_create", "tf_scheme_destroy", "tf_hook_set_dirichlet",
@@ -177,6 +179,15 @@ def context(device=None):
         check(lib().tf_ctx_create(device, C.byref(h)))
         _ctx[device] = h
     return _ctx[device]
+
+
+def new_context(device=None):
+    """An additional context (own stream) on a device; the caller keeps the handle."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    h = C.c_void_p()
+    check(lib().tf_ctx_create(device, C.byref(h)))
+    return h
 
 
 _pinned = []

@@ -36,11 +36,13 @@ def default_chunk_nodes(nvar, half_width):
 class DeviceState:
     """Fields of ``batch`` systems resident on the device."""
 
-    def __init__(self, cmodel, variant, N, batch, periodic):
+    def __init__(self, cmodel, variant, N, batch, periodic, ctx=None):
         self.cmodel, self.variant = cmodel, variant
+        self.ctx = cmodel.ctx if ctx is None else ctx     # stream the state's work runs on
         self.N, self.batch, self.periodic = int(N), int(batch), bool(periodic)
         self.h = C.c_void_p()
-        _lib.check(_lib.lib().tf_state_create(cmodel.ctx, variant.handle, self.N, self.batch,
+        handle = variant.handle                            # loads the cubin on first use
+        _lib.check(_lib.lib().tf_state_create(self.ctx, handle, self.N, self.batch,
                                               int(self.periodic), C.byref(self.h)))
         self._x = None
         self._consts = None
@@ -180,9 +182,9 @@ class CompiledModel:
             self._variants[node_pars] = Variant(self, node_pars)
         return self._variants[node_pars]
 
-    def new_state(self, pars, N, batch, periodic):
+    def new_state(self, pars, N, batch, periodic, ctx=None):
         v = self.variant(self.node_pars_of(pars, N, batch))
-        return DeviceState(self, v, N, batch, periodic)
+        return DeviceState(self, v, N, batch, periodic, ctx=ctx)
 
     def cached_state(self, pars, N, periodic):
         v = self.variant(self.node_pars_of(pars, N, 1))

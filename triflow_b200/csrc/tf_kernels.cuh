@@ -283,21 +283,37 @@ done:
 
 // Exclusive prefix of every thread's element over (lane, warp, tile) order.
 // `carry` is the prefix of the tile when look-back is disabled (single tile, or the
-// border kernel's sequential tile loop).
+// border kernel's sequential tile loop).  `reuse`: the shared scratch was used by an
+// earlier scan of the same kernel (needs a barrier before it is overwritten).
+//
+// Single tile without a tile total: after ONE barrier every warp scans the warp totals
+// itself (redundantly), so no warp waits for warp 0.  With look-back, warp 0 resolves
+// the tile prefix and the others wait for it.
 template <class Mon>
 __device__ Mon tile_scan(const Mon& mine, double* smem /* (MAXW+1)*K doubles */, bool use_lookback,
                          const Buf& b, long long gbase, int tile, int epoch, const Mon& carry,
-                         Mon* tile_total) {
+                         Mon* tile_total, bool reuse = false) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const Mon incl = warp_scan(mine, lane);
   Mon excl = shfl_up(incl, 1);
   excl = select(lane == 0, Mon::identity(), excl);
-  __syncthreads();                         // smem reuse across successive scans
+  if (reuse) __syncthreads();
   if (lane == 31) {
 #pragma unroll
     for (int k = 0; k < Mon::K; ++k) smem[warp * Mon::K + k] = incl.d[k];
   }
   __syncthreads();
+  if (!use_lookback && tile_total == nullptr) {
+    Mon w = Mon::identity();
+    if (lane < nwarps) {
+#pragma unroll
+      for (int k = 0; k < Mon::K; ++k) w.d[k] = smem[lane * Mon::K + k];
+    }
+    const Mon wi = warp_scan(w, lane);
+    Mon we = shfl_idx(wi, warp > 0 ? warp - 1 : 0);
+    we = select(warp == 0, Mon::identity(), we);
+    return Mon::combine(Mon::combine(carry, we), excl);
+  }
   if (warp == 0) {
     Mon w = Mon::identity();
     if (lane < nwarps) {
@@ -998,7 +1014,7 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_border_fill(Geom g, Buf b,
           carry.c()[t] = v;
         }
         Aff total;
-        const Aff pre = tile_scan<Aff>(mine, smem, false, b, 0, 0, 0, carry, &total);
+        const Aff pre = tile_scan<Aff>(mine, smem, false, b, 0, 0, 0, carry, &total, true);
 #pragma unroll
         for (int t = 0; t < BETA; ++t)
 #pragma unroll

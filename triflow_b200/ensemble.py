@@ -24,7 +24,7 @@ class Ensemble:
     """
 
     def __init__(self, model, scheme, x, fields, pars, hook=null_hook, batch=None,
-                 reuse_constant_factor=False):
+                 reuse_constant_factor=False, ctx=None):
         self.model, self.scheme = model, scheme
         cm = model._cuda
         x = np.asarray(x, dtype=np.float64)
@@ -37,7 +37,7 @@ class Ensemble:
         self.batch, self.N = int(batch), N
         self.nvar = model._nvar
         self.pars = dict(pars)
-        self.state = cm.new_state(pars, N, self.batch, bool(pars["periodic"]))
+        self.state = cm.new_state(pars, N, self.batch, bool(pars["periodic"]), ctx=ctx)
         named = {h: fields[h] for h in model._help_funcs}
         self.state.set_inputs(x, named, pars)
         u = np.stack([np.broadcast_to(np.asarray(fields[v], dtype=np.float64),
@@ -104,7 +104,92 @@ class Ensemble:
         return {v: cols[:, e].copy() for e, v in enumerate(self.model._dep_vars)}
 
     def sync(self):
-        _lib.check(_lib.lib().tf_ctx_sync(self.state.cmodel.ctx))
+        _lib.check(_lib.lib().tf_ctx_sync(self.state.ctx))
 
 
-__all__ = ["Ensemble", "Dirichlet"]
+def _members(v, lo, hi, batch, N):
+    """Slice the member axis of a field / parameter value (same shapes as Ensemble)."""
+    if np.ndim(v) == 2:
+        return np.asarray(v)[lo:hi]
+    if np.ndim(v) == 1 and np.shape(v)[0] == batch and batch != N:
+        return np.asarray(v)[lo:hi]
+    return v
+
+
+class HostPipeline:
+    """Ensemble stepped from / to host buffers: ``upload -> step -> download``.
+
+    This is the reference's calling convention (``scheme(t, fields, dt, pars)`` takes and
+    returns host fields, ``core/schemes.py:102-135``) for a whole ensemble.  The members
+    are split into ``groups`` contiguous blocks, each on its own context (stream) in
+    asynchronous mode, so the PCIe upload of one block, the stepping of another and the
+    download of a third proceed together; with pinned buffers (``_lib.pinned_empty``) a
+    call costs about ``max(upload, download)`` instead of their sum plus the step.
+    """
+
+    def __init__(self, model, scheme, x, fields, pars, hook=null_hook, batch=None, groups=8):
+        x = np.asarray(x, dtype=np.float64)
+        N = x.size
+        if batch is None:
+            batch = 1
+            for v in list(fields.values()) + [pars[p] for p in model._pars]:
+                if np.ndim(v) == 2 or (np.ndim(v) == 1 and np.shape(v)[0] != N):
+                    batch = max(batch, np.shape(v)[0])
+        self.batch, self.N, self.nvar = int(batch), N, model._nvar
+        groups = max(1, min(int(groups), self.batch))
+        edges = [self.batch * g // groups for g in range(groups + 1)]
+        self.ranges = [(lo, hi) for lo, hi in zip(edges[:-1], edges[1:]) if hi > lo]
+        lib = _lib.lib()
+        self.parts = []
+        for lo, hi in self.ranges:
+            ctx = _lib.new_context()
+            f = {k: _members(v, lo, hi, self.batch, N) for k, v in fields.items()}
+            p = {k: (_members(v, lo, hi, self.batch, N) if k != "periodic" else v)
+                 for k, v in pars.items()}
+            part = Ensemble(model, scheme, x, f, p, hook=hook, batch=hi - lo, ctx=ctx)
+            part.sync()
+            _lib.check(lib.tf_ctx_set_async(ctx, 1))
+            self.parts.append(part)
+        self.scheme = scheme
+        self.t = 0.0
+
+    def step_host(self, u_in, u_out, dt, n_steps=1):
+        """``u_in`` -> ``n_steps`` fixed steps -> ``u_out``; both ``(batch, N*nvar)`` in the
+        ``uflat`` layout, C-contiguous float64 (pinned for overlap)."""
+        lib = _lib.lib()
+        width = self.N * self.nvar
+        u_in = np.asarray(u_in).reshape(self.batch, width)
+        u_out = np.asarray(u_out).reshape(self.batch, width)
+        for (lo, hi), part in zip(self.ranges, self.parts):
+            _lib.check(lib.tf_state_upload(part.state.h, None, _lib.dptr(u_in[lo:hi]), None,
+                                           None, None))
+            _lib.check(lib.tf_scheme_step(part.state.h, self.scheme.handle, float(dt),
+                                          int(n_steps), None))
+            _lib.check(lib.tf_state_download(part.state.h, _lib.dptr(u_out[lo:hi])))
+        self.sync()
+        self.t += n_steps * dt
+        return u_out
+
+    def sync(self):
+        """Wait for every block; raises if a factorisation failed (as the blocking API)."""
+        for part in self.parts:
+            part.sync()
+        for (lo, hi), part in zip(self.ranges, self.parts):
+            bad = np.flatnonzero(part.state.status())
+            if bad.size:
+                raise RuntimeError("banded factorisation failed for system %d (status %d)"
+                                   % (lo + bad[0], part.state.status()[bad[0]]))
+
+    def launch_count(self):
+        lib = _lib.lib()
+        return sum(lib.tf_ctx_launch_count(p.state.ctx) for p in self.parts)
+
+    def close(self):
+        for part in self.parts:
+            part.sync()
+            part.state.close()
+            _lib.lib().tf_ctx_destroy(part.state.ctx)
+        self.parts = []
+
+
+__all__ = ["Ensemble", "HostPipeline", "Dirichlet"]
