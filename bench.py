@@ -45,6 +45,8 @@ def kernel_bytes(wk, family, stage=None):
     §8d step model split over the launches (DESIGN.md 'Roofline accounting')."""
     v, w, s = wk["v"], wk["w"], wk["s"]
     B = v * v * w
+    if family == "sysstep":                      # whole step in one launch (system-resident path)
+        return wk["Q"]
     if family == "factor":
         return 8 * (B + v)                       # write factor, read U
     lshare = B * (w // 2) / w                    # L part of the factor

@@ -397,6 +397,7 @@ def test_factor_reuse_is_bit_identical_for_constant_jacobian():
         ens = Ensemble(m, S.ROS3PRw(m, **FX), c["x"], c["fields"], c["pars"],
                        hook=S.Dirichlet(U=(1.0, 0.0)), batch=len(mem),
                        reuse_constant_factor=reuse)
+        ens.set_fusion(False)           # the kept factor lives in HBM: per-kernel pipeline
         ens.step(c["dt"], 12)
         out.append(ens.download())
     assert np.array_equal(out[0], out[1])
@@ -404,6 +405,45 @@ def test_factor_reuse_is_bit_identical_for_constant_jacobian():
         km = gmodel("ks")
         ck = W.kuramoto(1024)
         Ensemble(km, S.ROS2(km), ck["x"], ck["fields"], ck["pars"], reuse_constant_factor=True)
+
+
+@pytest.mark.parametrize("sname,kw", [("ROS3PRw", FX), ("ROS2", {}), ("Theta", dict(theta=1)),
+                                      ("Theta", dict(theta=0.5))])
+@pytest.mark.parametrize("mname,N", [("advdiff", 200), ("advdiff", 1000), ("advdiff", 4096),
+                                     ("burgers_up1", 777)])
+def test_system_resident_step_equals_kernel_pipeline(sname, kw, mname, N):
+    """The one-launch step (system in shared memory, factor in registers) runs the
+    algorithm of the per-kernel pipeline with the same chunking and scan trees; the two
+    cubin kernels differ only in where ptxas contracts a*b+c into an FMA (identical bits
+    with -fmad=false), so they agree to rounding: <= 1e-12 of the solution range after 8
+    steps, and the embedded error estimate to 1e-9 relative."""
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.ensemble import Ensemble
+    m = gmodel(mname)
+    rng = np.random.default_rng(5)
+    batch = 37
+    if mname == "advdiff":
+        c = W.ensemble(N, np.arange(0, 32768, 900)[:batch])
+        x, pars, dt = c["x"], c["pars"], c["dt"]
+        hook = S.Dirichlet(U=(1.0, 0.0))
+    else:
+        x = np.arange(N) * 0.2
+        pars = dict(k=np.linspace(0.05, 0.3, batch), periodic=False)
+        dt, hook = 0.1, S.null_hook
+    U0 = np.cos(2 * np.pi * 5 * x / x[-1]) + 0.3 * rng.standard_normal((batch, N))
+    out = []
+    for fused in (True, False):
+        ens = Ensemble(m, getattr(S, sname)(m, **kw), x, dict(U=U0), pars, hook=hook, batch=batch)
+        ens.set_fusion(fused)
+        e1 = ens.step(dt, 1, want_err=True)
+        e7 = ens.step(dt, 7, want_err=True)
+        out.append((ens.download(), e1, e7))
+        assert not ens.state.status().any()
+    assert np.isfinite(out[0][0]).all()
+    for r in range(batch):
+        assert rel_traj_err(out[0][0][r], out[1][0][r]) <= 1e-12
+    for k in (1, 2):
+        assert np.allclose(out[0][k], out[1][k], rtol=1e-9, atol=0, equal_nan=True)
 
 
 # ------------------------------------------- BASELINE.json full sizes vs the oracle

@@ -22,7 +22,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 TF_OK, TF_EINVAL, TF_ECUDA, TF_EMAXITER, TF_EDTMIN, TF_ESINGULAR = range(6)
 FAMILIES = ["factor", "border_fill", "fwd", "border_solve", "bwd", "update", "hook",
-            "pack", "eval"]
+            "pack", "eval", "sysstep"]
 
 
 class CudaUnavailable(RuntimeError):
@@ -67,7 +67,7 @@ def build_library(force=False):
     return LIB_PATH
 
 
-_KERNEL_SRCS = ["tf_kernels.cuh", "tf_band.h", "tf_params.h", "tf_model_prelude.h"]
+_KERNEL_SRCS = ["tf_kernels.cuh", "tf_sysstep.cuh", "tf_band.h", "tf_params.h", "tf_model_prelude.h"]
 
 
 def build_cubin(header, chunk_nodes, warps, fast_div=False):
@@ -120,6 +120,7 @@ def lib():
         "tf_scheme_step": [vp, vp, d, i, dp],
         "tf_scheme_advance": [vp, vp, d, d, d, d, i, d, i, dp, C.POINTER(i), dp],
         "tf_state_status": [vp, C.POINTER(i)], "tf_state_set_factor_reuse": [vp, i],
+        "tf_state_set_fusion": [vp, i],
         "tf_ensemble_advance": [vp, vp, d, d, d, d, i, d, dp, C.POINTER(i), C.POINTER(i)],
         "tf_ctx_timer_start": [vp], "tf_ctx_timer_stop": [vp, C.POINTER(C.c_float)],
         "tf_ctx_profile": [vp, i],
@@ -141,7 +142,7 @@ EXPORTS = ["tf_last_error", "tf_ctx_create", "tf_ctx_destroy", "tf_ctx_sync", "t
            "tf_state_destroy", "tf_state_upload", "tf_state_download", "tf_eval_F",
            "tf_eval_J", "tf_scheme_create", "tf_scheme_destroy", "tf_hook_set_dirichlet",
            "tf_hook_clear", "tf_scheme_step", "tf_scheme_advance", "tf_state_status",
-           "tf_state_set_factor_reuse", "tf_ensemble_advance",
+           "tf_state_set_factor_reuse", "tf_state_set_fusion", "tf_ensemble_advance",
            "tf_ctx_launch_count", "tf_ctx_timer_start", "tf_ctx_timer_stop",
            "tf_ctx_profile", "tf_ctx_profile_read"]
 

@@ -1085,7 +1085,7 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_border_fill(Geom g, Buf b,
 #pragma unroll
       for (int i = 0; i < NB; ++i)
 #pragma unroll
-        for (int j = 0; j < NB; ++j) part[i][j] += gv[i] * wv[j];
+        for (int j = 0; j < NB; ++j) part[i][j] = __fma_rn(gv[i], wv[j], part[i][j]);
     }
   }
 #pragma unroll
@@ -1104,7 +1104,7 @@ extern "C" __global__ void __launch_bounds__(NT) tf_k_border_fill(Geom g, Buf b,
       for (int j = 0; j < NB; ++j) {
         double v = 0.0;
         for (int w = 0; w < nwarps; ++w) v += s_red[w][i * NB + j];
-        S[i * NB + j] = ((i == j) ? 1.0 : 0.0) - a * bt[4 * NB * NB + i * NB + j] - v;
+        S[i * NB + j] = __dsub_rn(__fma_rn(-a, bt[4 * NB * NB + i * NB + j], (i == j) ? 1.0 : 0.0), v);
         I[i * NB + j] = (i == j) ? 1.0 : 0.0;
       }
     tfb::solve_inplace<NB, NB>(S, I);
@@ -1296,10 +1296,12 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
 #pragma unroll
       for (int e = 0; e < V; ++e) {
         const int r = m * V + e;
-        double rhs = dt * fe[e];
+        // explicit roundings: the system-resident kernel (tf_sysstep.cuh) must contract alike
+        double rhs = __dmul_rn(dt, fe[e]);
 #pragma unroll
         for (int q = 0; q < (NPREV < 0 ? MAXS : NPREV); ++q)
-          if (NPREV >= 0 || q < st.nprev) rhs += st.cfac[q] * b.K[q][sys * vs + cb + (long long)r * 32];
+          if (NPREV >= 0 || q < st.nprev)
+            rhs = __fma_rn(st.cfac[q], b.K[q][sys * vs + cb + (long long)r * 32], rhs);
         rhs = (i < g.N) ? rhs : 0.0;
         sF[sb + r * 32] = rhs;
         double coef[BETA];
@@ -1389,18 +1391,18 @@ __device__ __forceinline__ void border_solution_partials(double (&xb)[NB], const
     for (int r = g.nhat - NB; r < g.nhat; ++r) {       // natural coupling of the last rows
       const double yr = Y[ridx(r)];
 #pragma unroll
-      for (int c = 0; c < NB; ++c) acc[c] += G[fidx(r, c, NB)] * yr;
+      for (int c = 0; c < NB; ++c) acc[c] = __fma_rn(G[fidx(r, c, NB)], yr, acc[c]);
     }
   }
   double yb[NB];
 #pragma unroll
-  for (int c = 0; c < NB; ++c) yb[c] = Y[ridx(g.nhat + c)] - acc[c];
+  for (int c = 0; c < NB; ++c) yb[c] = __dsub_rn(Y[ridx(g.nhat + c)], acc[c]);
   const double* Si = b.Sinv + (long long)sys * NB * NB;
 #pragma unroll
   for (int r = 0; r < NB; ++r) {
     double s = 0.0;
 #pragma unroll
-    for (int c = 0; c < NB; ++c) s += Si[r * NB + c] * yb[c];
+    for (int c = 0; c < NB; ++c) s = __fma_rn(Si[r * NB + c], yb[c], s);
     xb[r] = s;
   }
 }
@@ -1557,7 +1559,7 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
       const int gr = r0 + r;
       if (fill_row(gr, wlead, g)) {
 #pragma unroll
-        for (int c = 0; c < NB; ++c) yv -= W[((long long)r * NB + c) * 32] * xb[c];
+        for (int c = 0; c < NB; ++c) yv = __fma_rn(-W[((long long)r * NB + c) * 32], xb[c], yv);
       } else if (gr >= g.nhat && gr < g.nhat + NB) {
 #pragma unroll
         for (int c = 0; c < NB; ++c) if (gr - g.nhat == c) yv = xb[c];
@@ -1603,7 +1605,7 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
       double kprev[NQ > 0 ? NQ : 1];
 #pragma unroll
       for (int q = 0; q < NQ; ++q)
-        if (NPREV >= 0 || q < st.nprev) { kprev[q] = b.K[q][sys * vs + a]; k -= st.cfac[q] * kprev[q]; }
+        if (NPREV >= 0 || q < st.nprev) { kprev[q] = b.K[q][sys * vs + a]; k = __fma_rn(-st.cfac[q], kprev[q], k); }
       if (!last) {
         Kout[(long long)r * 32] = k;
       } else {
@@ -1653,6 +1655,8 @@ TF_BWD_KERNEL(tf_k_bwd1n, 1, 0)
 TF_BWD_KERNEL(tf_k_bwd1l, 1, 1)
 TF_BWD_KERNEL(tf_k_bwd2l, 2, 1)
 TF_BWD_KERNEL(tf_k_bwdg, -1, -1)
+
+#include "tf_sysstep.cuh"
 
 // Dirichlet-style hook: U[var][0] = left, U[var][N-1] = right  (README.md:126-129)
 extern "C" __global__ void tf_k_dirichlet(Geom g, double* __restrict__ U, const double* __restrict__ dir,

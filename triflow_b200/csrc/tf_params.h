@@ -59,3 +59,16 @@ struct TfStage {
   double bp[TF_MAXS];
 };
 
+
+/* Whole-step descriptor of the system-resident kernel (tf_sysstep.cuh): every stage of
+   one ROW_general._fixed_step / Theta step (reference core/schemes.py:142-174,548-559). */
+struct TfStepDesc {
+  int s;                            /* stages (<= 3 on this path) */
+  int has_pred;
+  double dt;
+  double a;                         /* gamma_ii * dt */
+  double alpha[TF_MAXS][TF_MAXS];   /* U_i = U + sum_{j<i} alpha[i][j] k_j */
+  double cfac[TF_MAXS][TF_MAXS];    /* gamma_ij / gamma_ii */
+  double b[TF_MAXS];
+  double bp[TF_MAXS];
+};

@@ -1,0 +1,562 @@
+// System-resident implicit step: one CTA owns one whole system for the whole step.
+//
+// For ensembles of small systems (one system fits one CTA: N <= 32 * MAXW * M nodes,
+// config 5 of BASELINE.json) the per-kernel pipeline of tf_kernels.cuh moves
+// Q = 8[(1+s)B + (1+4s+s(s-1)/2)v] bytes per node and step through HBM (factor written
+// once, read once per stage, every stage vector written and read back).  None of this
+// has to leave the SM: here the state U and the stage vectors k_j live in shared memory,
+// the banded factor and the forward-substitution result live in the registers of the
+// thread that owns the rows, and a step reads U once and writes U+ once (16 bytes per
+// node instead of 224 for ROS3PRw).  The algorithm is the one of the per-kernel path
+// (same chunking, same scan trees); the two differ only in where ptxas contracts a*b+c
+// into an FMA (identical bits when built with -fmad=false), tests compare them to 1e-12.
+//
+// Replaces, in one launch (reference file:line): compute_J_numpy + I - gamma*dt*J +
+// factorized (compilers.py:292-332, schemes.py:146-149), the s stages of
+// ROW_general._fixed_step (schemes.py:150-163), update and error norm (:164-174), and the
+// Theta step (:548-559) as the one-stage case.
+//
+// Scope: scalar models with a tridiagonal Jacobian (V == 1, P == 1), non-periodic,
+// s <= 3 stages.  Everything else keeps the per-kernel path.
+#pragma once
+
+#if (TF_NVAR == 1) && (TF_P == 1)
+#define TF_HAS_SYSSTEP 1
+
+namespace tfk {
+
+constexpr int SYS_MAXK = 2;   // stage vectors kept in shared memory (s - 1 <= 2)
+
+// Exclusive prefix of every thread's element over the CTA (one tile, no look-back).
+// REV: the order runs from the last thread to the first (backward substitution); the
+// combine tree is the mirror image of the forward one, i.e. the tree the per-kernel
+// backward sweep builds with its reversed thread -> chunk assignment.
+template <class Mon, bool REV>
+__device__ __forceinline__ Mon cta_scan(const Mon& mine, double* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int ml = REV ? 31 - lane : lane;               // position in scan order
+  const int mw = REV ? nwarps - 1 - warp : warp;
+  Mon incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const Mon o = REV ? shfl_down(incl, d) : shfl_up(incl, d);
+    const Mon c = Mon::combine(o, incl);
+    incl = select(ml >= d, c, incl);
+  }
+  Mon excl = REV ? shfl_down(incl, 1) : shfl_up(incl, 1);
+  excl = select(ml == 0, Mon::identity(), excl);
+  __syncthreads();                                     // scratch of the previous scan is consumed
+  if (ml == 31) {
+#pragma unroll
+    for (int k = 0; k < Mon::K; ++k) smem[mw * Mon::K + k] = incl.d[k];
+  }
+  __syncthreads();
+  Mon w = Mon::identity();
+  if (lane < nwarps) {
+#pragma unroll
+    for (int k = 0; k < Mon::K; ++k) w.d[k] = smem[lane * Mon::K + k];
+  }
+  const Mon wi = warp_scan(w, lane);
+  Mon we = shfl_idx(wi, mw > 0 ? mw - 1 : 0);
+  we = select(mw == 0, Mon::identity(), we);
+  return Mon::combine(Mon::combine(Mon::identity(), we), excl);
+}
+
+struct SysShared {
+  double scan[(MAXW + 1) * KMAX];
+  double cst[NC2];
+  double lnext[NT * BETA * BETA];      // L multipliers a chunk leaves on the next chunk's rows
+  double tailL[NB * BETA];             // factor rows of the last NB interior unknowns
+  double tailU[NB * (BETA + 1)];
+  double W[NB * NB], G[NB * NB], Sinv[NB * NB];
+  double ytail[2 * NB];                // y of the last NB interior rows and of the border rows
+  double err[MAXW];
+  unsigned long long bar[2];
+};
+
+// ---- factorisation of the thread's rows into registers (factor_body_stream, V == 1)
+__device__ __forceinline__ void sys_factor(const Geom& g, const Buf& lb, int sys, double a,
+                                           const double* cst, SysShared& sh,
+                                           double (&Lr)[C][BETA], double (&Ur)[C][BETA + 1],
+                                           int& bad) {
+  constexpr int NODES = M + EX;
+  constexpr int NSB = C / BETA;
+  const int chunk = threadIdx.x;
+  const int i0 = chunk * M;
+  double win[NF][NODES + 2 * P];
+  Star mine = Star::identity();
+  const bool allreg = i0 >= P && i0 + NODES <= g.N - 2 * P;
+  load_windows<NODES, 0>(win, i0, g, lb, sys, nullptr);
+  {
+    double cur[BETA][WB], nxt[BETA][WB];
+#pragma unroll
+    for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, lb, sys, a, cst, allreg);
+#pragma unroll
+    for (int k = 0; k < NSB; ++k) {
+#pragma unroll
+      for (int r = 0; r < BETA; ++r)
+        node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, lb, sys, a, cst, allreg);
+      double Dh[BETA * BETA], Z[BETA * 2 * BETA], Rr[BETA * BETA];
+#pragma unroll
+      for (int r = 0; r < BETA; ++r)
+#pragma unroll
+        for (int c = 0; c < BETA; ++c) {
+          Dh[r * BETA + c] = cur[r][BETA + c - r] - mine.P()[r * BETA + c];
+          Z[r * 2 * BETA + c] = (c <= r) ? cur[r][BETA + BETA + c - r] : 0.0;
+          Z[r * 2 * BETA + BETA + c] = mine.Q()[r * BETA + c];
+          Rr[r * BETA + c] = (c >= r) ? nxt[r][BETA + c - BETA - r] : 0.0;
+        }
+      tfb::solve_inplace<BETA, 2 * BETA>(Dh, Z);
+      double Z1[BETA * BETA], Z2[BETA * BETA];
+#pragma unroll
+      for (int r = 0; r < BETA; ++r)
+#pragma unroll
+        for (int c = 0; c < BETA; ++c) {
+          Z1[r * BETA + c] = Z[r * 2 * BETA + c];
+          Z2[r * BETA + c] = Z[r * 2 * BETA + BETA + c];
+        }
+      Star nx;
+      tfb::mm<BETA>(Rr, Z1, nx.P());
+      tfb::mm<BETA>(Rr, Z2, nx.Q());
+#pragma unroll
+      for (int q = 0; q < BETA * BETA; ++q) nx.R()[q] = mine.R()[q];
+      tfb::mma<BETA>(mine.S(), Z2, nx.R());
+      tfb::mm<BETA>(mine.S(), Z1, nx.S());
+      mine = nx;
+#pragma unroll
+      for (int r = 0; r < BETA; ++r)
+#pragma unroll
+        for (int d = 0; d < WB; ++d) cur[r][d] = nxt[r][d];
+    }
+#pragma unroll
+    for (int q = 0; q < Star::K; ++q)
+      if (!(fabs(mine.d[q]) < 1e300)) bad = 1;
+  }
+  const Star pre = cta_scan<Star, false>(mine, sh.scan);
+  double X[BETA * BETA];
+#pragma unroll
+  for (int q = 0; q < BETA * BETA; ++q) X[q] = pre.P()[q];
+  double Lprev[BETA][BETA];
+#pragma unroll
+  for (int r = 0; r < BETA; ++r)
+#pragma unroll
+    for (int q = 0; q < BETA; ++q) Lprev[r][q] = 0.0;
+  double cur[BETA][WB], nxt[BETA][WB];
+#pragma unroll
+  for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, lb, sys, a, cst, allreg);
+#pragma unroll
+  for (int k = 0; k < NSB; ++k) {
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+      node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, lb, sys, a, cst, allreg);
+    double A2[2 * BETA][WB];
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int d = 0; d < WB; ++d) {
+        A2[r][d] = cur[r][d];
+        A2[BETA + r][d] = (BETA + r + d - BETA < BETA) ? nxt[r][d] : 0.0;
+      }
+    double Uf[BETA][BETA + 1], Lown[BETA][BETA], Lnext[BETA][BETA], Xo[BETA * BETA];
+    tfb::ChunkLU<BETA, BETA>::run2x(A2, X, Uf, Lown, Lnext, Xo, bad);
+#pragma unroll
+    for (int r = 0; r < BETA; ++r) {
+      const int row = k * BETA + r;
+#pragma unroll
+      for (int q = 0; q <= BETA; ++q) Ur[row][q] = Uf[r][q];
+#pragma unroll
+      for (int q = 1; q <= BETA; ++q) {
+        if (q <= r) Lr[row][q - 1] = Lown[r][q - 1];
+        else if (k > 0) Lr[row][q - 1] = Lprev[r][q - 1];
+        else Lr[row][q - 1] = 0.0;                // filled from the previous chunk below
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int q = 0; q < BETA; ++q) Lprev[r][q] = Lnext[r][q];
+#pragma unroll
+    for (int q = 0; q < BETA * BETA; ++q) X[q] = Xo[q];
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int d = 0; d < WB; ++d) cur[r][d] = nxt[r][d];
+  }
+  // multipliers of the next chunk's first BETA rows with respect to this chunk's pivots
+#pragma unroll
+  for (int r = 0; r < BETA; ++r)
+#pragma unroll
+    for (int q = 0; q < BETA; ++q) sh.lnext[(threadIdx.x * BETA + r) * BETA + q] = Lprev[r][q];
+  __syncthreads();
+  if (chunk > 0) {
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int q = r + 1; q <= BETA; ++q)
+        Lr[r][q - 1] = sh.lnext[((threadIdx.x - 1) * BETA + r) * BETA + q - 1];
+  }
+}
+
+// ---- border block of a non-periodic system: the natural coupling of the last NB
+//      interior rows to the border unknowns (bottom part of tf_k_border_fill)
+__device__ __forceinline__ void sys_border(const Geom& g, const Buf& b, int sys, double a,
+                                           SysShared& sh, const double (&Lr)[C][BETA],
+                                           const double (&Ur)[C][BETA + 1]) {
+  const int bot0 = g.nhat - NB;
+  const int r0 = threadIdx.x * C;
+  if (r0 + C > bot0 && r0 < g.nhat) {
+#pragma unroll
+    for (int r = 0; r < C; ++r) {
+      const int gr = r0 + r;
+      if (gr >= bot0 && gr < g.nhat) {
+#pragma unroll
+        for (int q = 0; q < BETA; ++q) sh.tailL[(gr - bot0) * BETA + q] = Lr[r][q];
+#pragma unroll
+        for (int q = 0; q <= BETA; ++q) sh.tailU[(gr - bot0) * (BETA + 1) + q] = Ur[r][q];
+      }
+    }
+  }
+  __syncthreads();                       // also orders the btab rows written by node_row
+  const double* bt = b.btab + (long long)sys * 5 * NB * NB;
+  if (threadIdx.x < 2 * NB) {
+    const bool isW = threadIdx.x < NB;
+    const int c = isW ? threadIdx.x : threadIdx.x - NB;
+    double loc[NB];
+    for (int j = 0; j < NB; ++j) {
+      double v = -(a * (isW ? bt[1 * NB * NB + j * NB + c] : bt[3 * NB * NB + c * NB + j]));
+      for (int q = 1; q <= BETA; ++q) {
+        const int jj = j - q;
+        if (jj < 0) break;
+        const double coef = isW ? sh.tailL[j * BETA + q - 1]
+                                : sh.tailU[(j - q) * (BETA + 1) + q] * sh.tailU[(j - q) * (BETA + 1)];
+        v -= coef * loc[jj];
+      }
+      loc[j] = v;
+      const double out = isW ? v : v * sh.tailU[j * (BETA + 1)];
+      (isW ? sh.W : sh.G)[j * NB + c] = 0.0 + out;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S[NB * NB], I[NB * NB];
+    for (int i = 0; i < NB; ++i)
+      for (int j = 0; j < NB; ++j) {
+        double v = 0.0;
+        for (int r = 0; r < NB; ++r) v = __fma_rn(sh.G[r * NB + i], sh.W[r * NB + j], v);
+        S[i * NB + j] = __dsub_rn(__fma_rn(-a, bt[4 * NB * NB + i * NB + j], (i == j) ? 1.0 : 0.0), v);
+        I[i * NB + j] = (i == j) ? 1.0 : 0.0;
+      }
+    tfb::solve_inplace<NB, NB>(S, I);
+    bool bad = false;
+    for (int k = 0; k < NB * NB; ++k) {
+      sh.Sinv[k] = I[k];
+      if (!(fabs(I[k]) < 1e300)) bad = true;
+    }
+    if (bad) atomicOr(b.status + sys, 2);
+  }
+  __syncthreads();
+}
+
+// ---- one Rosenbrock stage: forward substitution of dt*F(U_i) + sum cfac_j k_j, border
+//      solve, backward substitution; k_i -> shared memory, or (last stage) U+ -> HBM.
+template <int I, bool LAST>
+__device__ __forceinline__ void sys_stage(const Geom& g, const Buf& b, const Buf& lb, int sys,
+                                          const TfStepDesc& sd, double dt, const double* cst,
+                                          SysShared& sh, const double* sU, double* sK, double* sS,
+                                          const double (&Lr)[C][BETA], const double (&Ur)[C][BETA + 1],
+                                          double& emax) {
+  const int T = blockDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
+  const int chunk = threadIdx.x;
+  const int i0 = chunk * M;
+  const int sb = (warp * C) * 32 + lane;               // own chunk inside the system
+  const long long vs = vstride(g);
+  Stage st;
+  st.nprev = I;
+  st.istage = I;
+#pragma unroll
+  for (int q = 0; q < MAXS; ++q) {
+    st.alpha[q] = q < I ? sd.alpha[I][q] : 0.0;
+    st.cfac[q] = q < I ? sd.cfac[I][q] : 0.0;
+  }
+  double y[C];
+  // ---------------------------------------------------------------- forward
+  {
+    double own[C];
+#pragma unroll
+    for (int r = 0; r < C; ++r) own[r] = stage_value<I>(sU, lb, sys * vs, sb + (long long)r * 32, &st);
+    const double* sH = sU;                              // where neighbours find the stage state
+    if (I > 0) {
+#pragma unroll
+      for (int r = 0; r < C; ++r) sS[sb + r * 32] = own[r];
+      sH = sS;
+    }
+    double win[NF][M + 2 * P];
+    const bool interior = i0 >= P && i0 + M + P <= g.N && P <= M && NH == 0 && chunk > 0 &&
+                          chunk < T - 1;
+    if (!interior) {
+      Buf eb = lb;                                      // edge chunks: clamped window
+      eb.U = const_cast<double*>(sU) - sys * vs;
+      load_windows<M, I>(win, i0, g, eb, sys, &st);
+    }
+    if (I > 0) __syncthreads();
+    if (interior) {
+#pragma unroll
+      for (int w = 0; w < M + 2 * P; ++w) {
+        const int rel = w - P;
+        const int dc = rel < 0 ? -1 : (rel >= M ? 1 : 0);
+        const int m = rel - dc * M;
+        const int t2 = (int)threadIdx.x + dc;
+        const int nb = ((t2 >> 5) * C) * 32 + (t2 & 31);
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          win[e][w] = (dc == 0) ? own[(m * V + e) < C ? (m * V + e) : 0] : sH[nb + (m * V + e) * 32];
+      }
+    }
+    RecState rs;
+    rs.init();
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      const int i = i0 + m;
+      double fe[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) fe[e] = 0.0;
+      {                                   // padding nodes too (finite fill, rhs zeroed below)
+        TfNodeIn in;
+        node_inputs<M>(in, win, m, i, g, b, sys);
+        tf_model_F<FD>(cst, in, fe);
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const int r = m * V + e;
+        double rhs = __dmul_rn(dt, fe[e]);
+#pragma unroll
+        for (int q = 0; q < I; ++q) rhs = __fma_rn(st.cfac[q], sK[q * (T * C) + sb + r * 32], rhs);
+        rhs = (i < g.N) ? rhs : 0.0;
+        y[r] = rhs;
+        double coef[BETA];
+#pragma unroll
+        for (int q = 0; q < BETA; ++q) coef[q] = Lr[r][q];
+        rs.step(coef, rhs, 1.0);
+      }
+    }
+    Aff mine;
+    rs.to_map(mine);
+    const Aff pre = cta_scan<Aff, false>(mine, sh.scan);
+    double sv[BETA];
+#pragma unroll
+    for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
+#pragma unroll
+    for (int r = 0; r < C; ++r) {
+      double v = y[r];
+#pragma unroll
+      for (int q = 0; q < BETA; ++q) v -= Lr[r][q] * sv[q];
+#pragma unroll
+      for (int q = BETA - 1; q > 0; --q) sv[q] = sv[q - 1];
+      sv[0] = v;
+      y[r] = v;
+    }
+  }
+  // ------------------------------------------------- border solution x_b
+  const int r0 = chunk * C;
+  const int bot0 = g.nhat - NB;
+  const bool flagged = (r0 + C > g.nhat - NB && r0 < g.nhat + NB);
+  if (flagged) {
+#pragma unroll
+    for (int r = 0; r < C; ++r) {
+      const int gr = r0 + r;
+      if (gr >= bot0 && gr < g.nhat + NB) sh.ytail[gr - bot0] = y[r];
+    }
+  }
+  __syncthreads();
+  double xb[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) xb[c] = 0.0;
+  if (flagged) {
+    double acc[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) acc[c] = 0.0;
+    for (int r = 0; r < NB; ++r) {
+      const double yr = sh.ytail[r];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) acc[c] = __fma_rn(sh.G[r * NB + c], yr, acc[c]);
+    }
+    double yb[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) yb[c] = __dsub_rn(sh.ytail[NB + c], acc[c]);
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) s = __fma_rn(sh.Sinv[r * NB + c], yb[c], s);
+      xb[r] = s;
+    }
+  }
+  // --------------------------------------------------------------- backward
+  // border coupling of the few chunks that touch it: y <- y - W x_b on the fill rows,
+  // border rows <- x_b (applied once, ahead of both passes)
+  if (flagged) {
+#pragma unroll
+    for (int r = 0; r < C; ++r) {
+      const int gr = r0 + r;
+      double yv = y[r];
+      if (gr >= bot0 && gr < g.nhat) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) yv = __fma_rn(-sh.W[(gr - bot0) * NB + c], xb[c], yv);
+      } else if (gr >= g.nhat && gr < g.nhat + NB) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) if (gr - g.nhat == c) yv = xb[c];
+      }
+      y[r] = yv;
+    }
+  }
+  auto load_y = [&](int r) -> double { return y[r]; };
+  Aff mine;
+  {
+    RecState rs;
+    rs.init();
+#pragma unroll
+    for (int r = C - 1; r >= 0; --r) {
+      double coef[BETA];
+#pragma unroll
+      for (int q = 0; q < BETA; ++q) coef[q] = Ur[r][q + 1];
+      rs.step(coef, load_y(r), Ur[r][0]);
+    }
+    rs.to_map(mine);
+  }
+  const Aff pre = cta_scan<Aff, true>(mine, sh.scan);
+  double sv[BETA];
+#pragma unroll
+  for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
+#pragma unroll
+  for (int r = C - 1; r >= 0; --r) {
+    double v = load_y(r);
+#pragma unroll
+    for (int q = 0; q < BETA; ++q) v -= Ur[r][q + 1] * sv[q];
+    v *= Ur[r][0];
+#pragma unroll
+    for (int q = BETA - 1; q > 0; --q) sv[q] = sv[q - 1];
+    sv[0] = v;
+    double k = v;
+    double kprev[I > 0 ? I : 1];
+#pragma unroll
+    for (int q = 0; q < I; ++q) {
+      kprev[q] = sK[q * (T * C) + sb + r * 32];
+      k = __fma_rn(-st.cfac[q], kprev[q], k);
+    }
+    if (!LAST) {
+      sK[I * (T * C) + sb + r * 32] = k;
+    } else {
+      double acc = 0.0, accp = 0.0;
+#pragma unroll
+      for (int q = 0; q <= I; ++q) {
+        const double kq = (q < I) ? kprev[q < I ? q : 0] : k;
+        const double t = __dmul_rn(sd.b[q], kq);
+        acc = (q == 0) ? t : __dadd_rn(acc, t);
+        const double tp = __dmul_rn(sd.bp[q], kq);
+        accp = (q == 0) ? tp : __dadd_rn(accp, tp);
+      }
+      const double un = __dadd_rn(sU[sb + r * 32], acc);
+      b.Un[sys * vs + sb + (long long)r * 32] = un;
+      if (sd.has_pred) {
+        const double e = fabs(__dsub_rn(un, __dadd_rn(un, accp)));
+        emax = (e > emax || e != e) ? e : emax;
+      }
+    }
+  }
+  (void)nwarps;
+}
+
+}  // namespace tfk
+
+// One CTA per system, persistent over the systems of the batch (grid = resident CTAs).
+// The next system's U is fetched by a bulk asynchronous copy (TMA) while the current
+// one is stepped.
+extern "C" __global__ void __launch_bounds__(tfk::NT, 1) tf_k_sysstep(tfk::Geom g, tfk::Buf b,
+                                                                      TfStepDesc sd) {
+  using namespace tfk;
+  extern __shared__ __align__(128) double dsm_sys[];
+  double* dsm = dsm_sys;
+  __shared__ SysShared sh;
+  const int T = blockDim.x;
+  const int TC = T * C;                                  // doubles per vector of one system
+  double* sUb[2] = {dsm, dsm + TC};
+  double* sK = dsm + 2 * TC;                             // [SYS_MAXK][TC]
+  double* sS = dsm + (2 + SYS_MAXK) * TC;
+  const long long vs = vstride(g);
+  const unsigned bytes = (unsigned)(TC * sizeof(double));
+  if (threadIdx.x == 0) { mbar_init(&sh.bar[0], 1); mbar_init(&sh.bar[1], 1); }
+  __syncthreads();
+  unsigned phase[2] = {0u, 0u};
+  int it = 0;
+  auto is_active = [&](int s) { return b.active == nullptr || b.active[s] != 0; };
+  // first system of this CTA
+  int sys = blockIdx.x;
+  while (sys < g.batch && !is_active(sys)) sys += gridDim.x;
+  if (sys < g.batch && threadIdx.x == 0) {
+    mbar_expect_tx(&sh.bar[0], bytes);
+    bulk_g2s(sUb[0], b.U + sys * vs, bytes, &sh.bar[0]);
+  }
+  while (sys < g.batch) {
+    const int cur = it & 1;
+    int nxt = sys + gridDim.x;
+    while (nxt < g.batch && !is_active(nxt)) nxt += gridDim.x;
+    if (nxt < g.batch && threadIdx.x == 0) {             // buffer cur^1 was released by the
+      mbar_expect_tx(&sh.bar[cur ^ 1], bytes);           // barrier that ended the last system
+      bulk_g2s(sUb[cur ^ 1], b.U + nxt * vs, bytes, &sh.bar[cur ^ 1]);
+    }
+    const double a = (b.asys != nullptr) ? b.asys[sys] : sd.a;
+    const double dt = (b.dtsys != nullptr) ? b.dtsys[sys] : sd.dt;
+    for (int k = threadIdx.x; k < NC2; k += T) sh.cst[k] = b.cst[(long long)sys * NC2 + k];
+    const double* sU = sUb[cur];
+    Buf lb = b;                                          // U and k_j of this system: shared memory
+    lb.U = const_cast<double*>(sU) - sys * vs;
+#pragma unroll
+    for (int q = 0; q < SYS_MAXK; ++q) lb.K[q] = sK + q * TC - sys * vs;
+    mbar_wait(&sh.bar[cur], phase[cur]);
+    phase[cur] ^= 1u;
+    __syncthreads();
+    double Lr[C][BETA], Ur[C][BETA + 1];
+    int bad = 0;
+    sys_factor(g, lb, sys, a, sh.cst, sh, Lr, Ur, bad);
+    if (bad) atomicOr(b.status + sys, 1);
+    sys_border(g, b, sys, a, sh, Lr, Ur);
+    double emax = 0.0;
+    if (sd.s == 1) {
+      sys_stage<0, true>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+    } else {
+      sys_stage<0, false>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+      __syncthreads();
+      if (sd.s == 2) {
+        sys_stage<1, true>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+      } else {
+        sys_stage<1, false>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+        __syncthreads();
+        sys_stage<2, true>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+      }
+    }
+    // error estimate of the system
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (sd.has_pred) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, emax, d);
+        emax = (o > emax || o != o) ? o : emax;
+      }
+      if (lane == 0) sh.err[warp] = emax;
+    }
+    __syncthreads();                                     // releases sU[cur], sK, sS, sh.*
+    if (threadIdx.x == 0) {
+      double e = 0.0;
+      if (sd.has_pred) {
+        e = sh.err[0];
+        for (int w = 1; w < (T >> 5); ++w) e = (sh.err[w] > e || sh.err[w] != sh.err[w]) ? sh.err[w] : e;
+      }
+      b.err[sys] = e;
+    }
+    sys = nxt;
+    ++it;
+  }
+}
+
+#endif  // V == 1 && P == 1

@@ -56,6 +56,11 @@ class Ensemble:
             self.factor_reuse = True
         self.t = 0.0
 
+    def set_fusion(self, enable):
+        """System-resident stepping (one launch per step, state and factor kept on the SM)
+        on / off; off selects the per-kernel pipeline (same algorithm, agrees to rounding)."""
+        _lib.check(_lib.lib().tf_state_set_fusion(self.state.h, int(bool(enable))))
+
     def upload(self, u):
         """``u``: (batch, N*nvar) in uflat layout."""
         self.state.upload(u=np.asarray(u).reshape(self.batch, self.N * self.nvar))
