@@ -71,6 +71,9 @@ int tf_host_free(void* p);
 int tf_model_load(tf_ctx_t ctx, const void* cubin, size_t nbytes, const tf_model_desc* desc,
                   tf_model_t* out);
 int tf_model_unload(tf_model_t model);
+/* Introspection: copy a __device__ symbol of the model's cubin to the host (kernels built
+ * with -DTF_TRACE keep per-CTA phase time stamps in `tf_trace`; tools/trace_tiles.py). */
+int tf_model_read_symbol(tf_model_t model, const char* name, void* dst, size_t nbytes);
 
 /* Device-resident fields of `batch` independent systems of n_nodes nodes.
  * Replaces the per-call padding / view construction of init_computation_numpy

@@ -111,6 +111,7 @@ def lib():
         "tf_host_alloc": [C.c_size_t, C.POINTER(vp)], "tf_host_free": [vp],
         "tf_model_load": [vp, vp, C.c_size_t, C.POINTER(ModelDesc), C.POINTER(vp)],
         "tf_model_unload": [vp],
+        "tf_model_read_symbol": [vp, C.c_char_p, vp, C.c_size_t],
         "tf_state_create": [vp, vp, i, i, i, C.POINTER(vp)], "tf_state_destroy": [vp],
         "tf_state_upload": [vp, dp, dp, dp, dp, dp], "tf_state_download": [vp, dp],
         "tf_eval_F": [vp, dp], "tf_eval_J": [vp, dp],
@@ -138,7 +139,7 @@ def lib():
 
 EXPORTS = ["tf_last_error", "tf_ctx_create", "tf_ctx_destroy", "tf_ctx_sync", "tf_ctx_set_async",
            "tf_host_alloc",
-           "tf_host_free", "tf_model_load", "tf_model_unload", "tf_state_create",
+           "tf_host_free", "tf_model_load", "tf_model_unload", "tf_model_read_symbol", "tf_state_create",
            "tf_state_destroy", "tf_state_upload", "tf_state_download", "tf_eval_F",
            "tf_eval_J", "tf_scheme_create", "tf_scheme_destroy", "tf_hook_set_dirichlet",
            "tf_hook_clear", "tf_scheme_step", "tf_scheme_advance", "tf_state_status",

@@ -30,11 +30,31 @@
 #ifndef TF_FAST_DIV
 #define TF_FAST_DIV 0
 #endif
+#ifndef TF_LB_FIRST
+#define TF_LB_FIRST 4 /* look-back: predecessors awaited before the first evaluation */
+#endif
 #define TF_MAXW 16 /* max warps per CTA (runtime: blockDim.x / 32) */
 #ifndef TF_MINB
 /* min CTAs of 512 threads per SM for the sweep kernels: register cap 64 for narrow bands,
    128 for wide bands (their recurrence state alone is 60 doubles) */
 #define TF_MINB (((TF_P * TF_NVAR + TF_NVAR - 1) <= 2) ? 2 : 1)
+#endif
+
+// Optional per-CTA phase time stamps (build the cubin with -DTF_TRACE; tools/trace_tiles.py).
+// Slot = flag epoch of the chained launch (mod 16), 8 stamps (globaltimer ns) per CTA.
+#ifdef TF_TRACE
+__device__ unsigned long long tf_trace[16 * 4096 * 8];
+__device__ unsigned long long tf_trace2[16 * 4096 * 8];   // look-back rounds: [0..3] start ns, [4..7] ready run
+__device__ __forceinline__ void tf_stamp(int slot, int cta, int ph) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  tf_trace[(((slot) & 15) * 4096 + ((cta) & 4095)) * 8 + ph] = t;
+}
+#define TF_STAMP(slot, cta, ph) do { if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == 0) tf_stamp(slot, cta, ph); } while (0)
+#define TF_STAMP_LANE0(slot, cta, ph) do { if ((threadIdx.x & 31) == 0) tf_stamp(slot, cta, ph); } while (0)
+#else
+#define TF_STAMP(slot, cta, ph) do { } while (0)
+#define TF_STAMP_LANE0(slot, cta, ph) do { } while (0)
 #endif
 
 namespace tfk {
@@ -173,12 +193,17 @@ __device__ __forceinline__ Mon warp_reduce_rev(Mon v, int lane) {
   return v;
 }
 
-// flags are published with release and polled with acquire semantics (gpu scope):
-// orders the payload written by the same thread without a full fence / L1 flush
+// Flags are published with a release store and polled with RELAXED loads followed by one
+// acquire fence once the poll succeeded.  (ld.acquire.gpu compiles to LDG.STRONG.GPU +
+// CCTL.IVALL: every poll of a spin loop would invalidate the whole L1 of the SM, under the
+// feet of the co-resident CTAs.)  The payload itself is read with L1-bypassing loads.
 __device__ __forceinline__ int ld_flag(const int* p) {
   int v;
-  asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void acquire_fence() {
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void st_flag(int* p, int v) {
   asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -202,82 +227,126 @@ __device__ __forceinline__ bool absorbing(const Star& m) {
   return zq || zs;
 }
 
+// Look-back records: every value travels with its own tag in one 16-byte word (single
+// transaction, as in CUB's packed tile descriptors), so neither the publisher nor the
+// reader needs a memory fence: a record is valid once all its K words carry the tag.
+// (A release store costs a MEMBAR.ALL.GPU, an acquire load a CCTL.IVALL; measured with
+// tools/trace_tiles.py these fences made the look-back the longest phase of every sweep.)
+struct __align__(16) LbWord { double v; long long tag; };
+// Published with a 128-bit atomic exchange: atomics are performed at the L2, whereas plain
+// stores were observed (tools/trace_tiles.py) to become visible to the polling tiles up to
+// ~10 us late while their SM was busy.
+__device__ __forceinline__ void st_word(LbWord* p, double v, long long tag) {
+  long long o0, o1;
+  asm volatile(
+      "{\n.reg .b128 q, r;\nmov.b128 q, {%3, %4};\n"
+      "atom.relaxed.gpu.global.exch.b128 r, [%2], q;\nmov.b128 {%0, %1}, r;\n}"
+      : "=l"(o0), "=l"(o1)
+      : "l"(p), "l"(__double_as_longlong(v)), "l"(tag)
+      : "memory");
+  (void)o0; (void)o1;
+}
+__device__ __forceinline__ bool ld_word(const LbWord* p, double& v, long long tag) {
+  long long a, t;
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(t) : "l"(p) : "memory");
+  v = __longlong_as_double(a);
+  return t == tag;
+}
+template <class Mon>
+__device__ __forceinline__ void lb_publish(LbWord* dst, const Mon& m, long long tag, int lane) {
+#pragma unroll
+  for (int k0 = 0; k0 < Mon::K; k0 += 32) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (k0 + k < Mon::K && lane == k) v = m.d[(k0 + k < Mon::K) ? k0 + k : 0];
+    if (k0 + lane < Mon::K) st_word(dst + k0 + lane, v, tag);
+  }
+}
+template <class Mon>
+__device__ __forceinline__ bool lb_read(const LbWord* src, Mon& m, long long tag) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < Mon::K; ++k) ok = ld_word(src + k, m.d[k], tag) && ok;
+  return ok;
+}
+
 // Decoupled look-back over the tiles of one system.  Called by all 32 lanes of
-// warp 0 with the tile aggregate; returns the exclusive prefix of the tile.
-// Flags carry the launch epoch (no reset between launches): epoch*4 + {1: aggregate
-// published, 2: inclusive prefix published}.  The walk stops at the nearest
+// warp 0 with the tile aggregate (the same value in every lane); returns the exclusive
+// prefix of the tile.  Records carry the launch epoch (no reset between launches):
+// tag = epoch*4 + {1: aggregate, 2: inclusive prefix}.  The walk stops at the nearest
 // inclusive prefix, at the start of the system, or as soon as the accumulated
 // aggregate is absorbing (its propagator underflowed to exactly zero), which for
 // well-conditioned systems happens after a few tiles.
 template <class Mon>
 __device__ Mon lookback(const Mon& aggregate, const Buf& b, long long gbase, int tile, int lane,
                         int epoch) {
-  int* flags = b.flags + 1 + gbase;
-  double* agg = b.lbagg + (gbase + tile) * KMAX;
-  double* inc = b.lbinc + (gbase + tile) * KMAX;
-  const int FA = epoch * 4 + 1, FI = epoch * 4 + 2;
+  LbWord* agg = (LbWord*)b.lbagg + (gbase + tile) * KMAX;
+  LbWord* inc = (LbWord*)b.lbinc + (gbase + tile) * KMAX;
+  const long long FA = epoch * 4LL + 1, FI = epoch * 4LL + 2;
   if (tile == 0) {
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < Mon::K; ++k) inc[k] = aggregate.d[k];
-      st_flag(flags + tile, FI);
-    }
+    lb_publish(inc, aggregate, FI, lane);
     return Mon::identity();
   }
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < Mon::K; ++k) agg[k] = aggregate.d[k];
-    st_flag(flags + tile, FA);
-  }
+  lb_publish(agg, aggregate, FA, lane);
   Mon prefix = Mon::identity();
   int look = tile - 1;
-  while (true) {
+  bool finished = false;
+#ifdef TF_TRACE
+  int tr_rounds = 0, tr_depth = 0;
+#endif
+  while (!finished) {
     const int t = look - lane;            // lane 0 = nearest predecessor
-    // wait for the nearest predecessor, then take whatever contiguous run is ready
-    int f = FI;
-    bool conclusive = false;
+    // Wait for the TF_LB_FIRST nearest predecessors (a few tiles usually make the
+    // aggregate absorbing) and evaluate the contiguous run that is ready; if that is not
+    // conclusive, wait for the whole window of 32 and evaluate again.  Every round costs
+    // two dependent memory round trips that queue behind the bulk loads of the sweep.
+    int need = TF_LB_FIRST;               // lanes below `need` wait for their tile
     Mon w;
-    for (int attempt = 0; attempt < 2 && !conclusive; ++attempt) {
+    while (true) {
+      Mon e = Mon::identity();
+      bool isI = true, ready = true;
       if (t >= 0) {
-        f = ld_flag(flags + t);
-        if (attempt == 0) {
-          if (lane == 0) while (f != FA && f != FI) f = ld_flag(flags + t);
-        } else {
-          while (f != FA && f != FI) f = ld_flag(flags + t);
-        }
+        const LbWord* pi = (const LbWord*)b.lbinc + (gbase + t) * KMAX;
+        const LbWord* pa = (const LbWord*)b.lbagg + (gbase + t) * KMAX;
+        do {                               // both records in one round trip
+          Mon ea;
+          isI = lb_read(pi, e, FI);
+          const bool isA = lb_read(pa, ea, FA);
+          if (!isI) e = ea;
+          ready = isI || isA;
+        } while (!ready && lane < need);
       }
-      const bool ready = (t < 0) || f == FA || f == FI;
       const unsigned mr = __ballot_sync(0xffffffffu, ready);
-      const unsigned m2 = __ballot_sync(0xffffffffu, ready && (t < 0 || f == FI));
+      const unsigned m2 = __ballot_sync(0xffffffffu, ready && isI);
       const int kr = (~mr == 0u) ? 32 : (__ffs(~mr) - 1);     // contiguous ready lanes
       const int kstop = __ffs(m2) - 1;                         // nearest inclusive (or start)
-      const int last = (kstop >= 0 && kstop < kr) ? kstop : kr - 1;
-      Mon e = Mon::identity();
-      if (t >= 0 && lane <= last) {
-        const double* src = ((f == FI) ? b.lbinc : b.lbagg) + (gbase + t) * KMAX;
-#pragma unroll
-        for (int k = 0; k < Mon::K; ++k) e.d[k] = __ldcg(src + k);
-      }
+      const bool hit = (kstop >= 0 && kstop < kr);
+      const int last = hit ? kstop : kr - 1;
+      e = select(t >= 0 && lane <= last, e, Mon::identity());
       w = warp_reduce_rev(e, lane);
       w = shfl_idx(w, 0);
-      const bool hit = (kstop >= 0 && kstop < kr);
-      const bool absb = absorbing(w);
-      conclusive = hit || absb || kr == 32;
-      if (hit || absb) {
-        prefix = Mon::combine(w, prefix);
-        goto done;
+#ifdef TF_TRACE
+      if (lane == 0 && tr_rounds < 4) {
+        unsigned long long tn;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn));
+        tf_trace2[(((epoch) & 15) * 4096 + ((tile) & 4095)) * 8 + tr_rounds] = tn;
+        tf_trace2[(((epoch) & 15) * 4096 + ((tile) & 4095)) * 8 + 4 + tr_rounds] = kr * 100 + (hit ? 50 : 0) + (absorbing(w) ? 1 : 0);
       }
+      tr_rounds += 1;
+      if (hit || absorbing(w) || kr == 32) tr_depth += last + 1;
+#endif
+      if (hit || absorbing(w)) { finished = true; break; }
+      if (kr == 32) break;                // full window of aggregates: go further back
+      need = 32;                          // not conclusive: wait for the whole window
     }
-    prefix = Mon::combine(w, prefix);     // full window of 32 aggregates, go further back
+    prefix = Mon::combine(w, prefix);
     look -= 32;
   }
-done:
-  if (lane == 0) {
-    const Mon incl = Mon::combine(prefix, aggregate);
-#pragma unroll
-    for (int k = 0; k < Mon::K; ++k) inc[k] = incl.d[k];
-    st_flag(flags + tile, FI);
-  }
+#ifdef TF_TRACE
+  if (lane == 0) tf_trace[(((epoch) & 15) * 4096 + ((tile) & 4095)) * 8 + 2] = tr_rounds * 1000 + tr_depth;
+#endif
+  lb_publish(inc, Mon::combine(prefix, aggregate), FI, lane);
   return prefix;
 }
 
@@ -325,7 +394,9 @@ __device__ Mon tile_scan(const Mon& mine, double* smem /* (MAXW+1)*K doubles */,
     we = select(lane == 0, Mon::identity(), we);
     const Mon total = shfl_idx(wi, nwarps - 1);
     Mon tp = carry;
+    TF_STAMP_LANE0(epoch, tile, 4);
     if (use_lookback) tp = lookback(total, b, gbase, tile, lane, epoch);
+    TF_STAMP_LANE0(epoch, tile, 5);
     const Mon wp = Mon::combine(tp, we);
     __syncwarp();
     if (lane < nwarps) {
@@ -366,8 +437,8 @@ __device__ __forceinline__ void resolve_tile(const Geom& g, const Buf& b, int& s
   __shared__ unsigned s_ticket;
   __shared__ int s_epoch;
   if (threadIdx.x == 0) {
-    s_epoch = *((volatile int*)(b.ctl + 0));
-    const unsigned base = *((volatile unsigned*)(b.ctl + 1));
+    s_epoch = ld_flag(b.ctl + 0);
+    const unsigned base = (unsigned)ld_flag(b.ctl + 1);
     s_ticket = atomicAdd((unsigned*)b.flags, 1u) - base;
   }
   __syncthreads();
@@ -1218,6 +1289,7 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
   int sys, tile, epoch;
   resolve_tile(g, b, sys, tile, epoch);
   if (b.active != nullptr && !b.active[sys]) return;       // finished ensemble member
+  TF_STAMP(epoch, tile, 0);
   const double dt = (b.dtsys != nullptr) ? b.dtsys[sys] : st.dt;
   const int T = blockDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
@@ -1278,6 +1350,7 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
     }
   }
   __syncthreads();                         // every halo has been read: sS becomes sF
+  TF_STAMP(epoch, tile, 1);
   if (active) {
     mbar_wait(&s_bar, 0);
     RecState rs;
@@ -1312,8 +1385,10 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
     }
     rs.to_map(mine);
   }
+  TF_STAMP(epoch, tile, 3);
   const Aff pre = tile_scan<Aff>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
                                  epoch, Aff::identity(), nullptr);
+  TF_STAMP(epoch, tile, 6);
   // second pass with the true incoming state; when the border fill of this step is
   // already complete (every stage but the first) the tile also reduces its share of G^T y
   const int tile_rows = nwarps * 32 * C;
@@ -1360,6 +1435,7 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
       b.gpart[((long long)sys * g.tiles + tile) * NB + threadIdx.x] = v;
     }
   }
+  TF_STAMP(epoch, tile, 7);
   finish_chain(g, b, epoch);
 }
 
@@ -1550,6 +1626,7 @@ __device__ __forceinline__ void bwd_body(const Geom& g, const Buf& b, const Stag
   } else if (flagged) {
     const int* fl = (const int*)(b.xb + (long long)sys * (NB + 1) + NB);
     while (ld_flag(fl) != epoch) {}
+    acquire_fence();
 #pragma unroll
     for (int c = 0; c < NB; ++c) xb[c] = __ldcg(b.xb + (long long)sys * (NB + 1) + c);
   }

@@ -33,14 +33,14 @@ struct TfBuf {
   int* lead;            /* [batch][2] leading rows of W / G that may be non-zero */
   int* status;          /* [batch] bit0: bad pivot, bit1: singular border block */
   double* err;          /* [batch] embedded error estimate of the last step */
-  int* flags;           /* look-back: [0] ticket counter, then [batch*tiles] flags */
+  int* flags;           /* [0] ticket counter of the chained launches */
   int* ctl;             /* device-side launch bookkeeping: [0] epoch, [1] ticket base, [2] CTAs done */
   /* per-member adaptive stepping of ensembles (NULL: one dt for all systems) */
   const double* dtsys;  /* [batch] time step of this attempt */
   const double* asys;   /* [batch] gamma_ii * dt of this attempt */
   const int* active;    /* [batch] 0: member finished, its CTAs return immediately */
-  double* lbagg;        /* [batch*tiles][KMAX] tile aggregates */
-  double* lbinc;        /* [batch*tiles][KMAX] inclusive prefixes */
+  double* lbagg;        /* [batch*tiles][KMAX] tile aggregates, 16-byte (value, tag) words */
+  double* lbinc;        /* [batch*tiles][KMAX] inclusive prefixes, same format */
   double* gpart;        /* [batch*fwd_tiles][NB] per-tile partial G^T y of the last fwd */
 };
 
