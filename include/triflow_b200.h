@@ -144,11 +144,12 @@ int tf_ensemble_advance(tf_state_t st, tf_scheme_t sc, double t, double dt, doub
 int tf_state_set_factor_reuse(tf_state_t st, int enable);
 
 /* System-resident stepping (on by default): when a whole system fits one CTA (tridiagonal
- * scalar model, non-periodic, <= 3 stages, N <= 4096) one launch does the whole step of
+ * scalar model, non-periodic, N <= 4096 and (stages + 2) vectors of the system within 200 KB
+ * of shared memory) one launch does the whole step of
  * ROW_general._fixed_step (core/schemes.py:142-174) with U and the stage vectors in shared
  * memory and the factor in registers; 0 selects the per-kernel pipeline (same algorithm,
  * results agree to rounding). */
-int tf_state_set_fusion(tf_state_t st, int enable);
+int tf_state_set_fusion(tf_state_t st, int enable);   /* 2: on, run-time stage kernel for every tableau */
 
 /* status bits per system (bit0 bad pivot, bit1 singular border block) */
 int tf_state_status(tf_state_t st, int* status);

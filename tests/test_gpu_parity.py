@@ -408,7 +408,7 @@ def test_factor_reuse_is_bit_identical_for_constant_jacobian():
 
 
 @pytest.mark.parametrize("sname,kw", [("ROS3PRw", FX), ("ROS2", {}), ("Theta", dict(theta=1)),
-                                      ("Theta", dict(theta=0.5))])
+                                      ("Theta", dict(theta=0.5)), ("ROS3PRL", FX), ("RODASPR", FX)])
 @pytest.mark.parametrize("mname,N", [("advdiff", 200), ("advdiff", 1000), ("advdiff", 4096),
                                      ("burgers_up1", 777)])
 def test_system_resident_step_equals_kernel_pipeline(sname, kw, mname, N):
@@ -432,7 +432,7 @@ def test_system_resident_step_equals_kernel_pipeline(sname, kw, mname, N):
         dt, hook = 0.1, S.null_hook
     U0 = np.cos(2 * np.pi * 5 * x / x[-1]) + 0.3 * rng.standard_normal((batch, N))
     out = []
-    for fused in (True, False):
+    for fused in (True, False, "rt"):       # "rt": the run-time-stage variant of the kernel
         ens = Ensemble(m, getattr(S, sname)(m, **kw), x, dict(U=U0), pars, hook=hook, batch=batch)
         ens.set_fusion(fused)
         e1 = ens.step(dt, 1, want_err=True)
@@ -440,10 +440,11 @@ def test_system_resident_step_equals_kernel_pipeline(sname, kw, mname, N):
         out.append((ens.download(), e1, e7))
         assert not ens.state.status().any()
     assert np.isfinite(out[0][0]).all()
-    for r in range(batch):
-        assert rel_traj_err(out[0][0][r], out[1][0][r]) <= 1e-12
-    for k in (1, 2):
-        assert np.allclose(out[0][k], out[1][k], rtol=1e-9, atol=0, equal_nan=True)
+    for alt in (0, 2):
+        for r in range(batch):
+            assert rel_traj_err(out[alt][0][r], out[1][0][r]) <= 1e-12
+        for k in (1, 2):
+            assert np.allclose(out[alt][k], out[1][k], rtol=1e-9, atol=0, equal_nan=True)
 
 
 # ------------------------------------------- BASELINE.json full sizes vs the oracle

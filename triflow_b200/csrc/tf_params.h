@@ -63,7 +63,7 @@ struct TfStage {
 /* Whole-step descriptor of the system-resident kernel (tf_sysstep.cuh): every stage of
    one ROW_general._fixed_step / Theta step (reference core/schemes.py:142-174,548-559). */
 struct TfStepDesc {
-  int s;                            /* stages (<= 3 on this path) */
+  int s;                            /* stages */
   int has_pred;
   double dt;
   double a;                         /* gamma_ii * dt */

@@ -16,16 +16,15 @@
 // ROW_general._fixed_step (schemes.py:150-163), update and error norm (:164-174), and the
 // Theta step (:548-559) as the one-stage case.
 //
-// Scope: scalar models with a tridiagonal Jacobian (V == 1, P == 1), non-periodic,
-// s <= 3 stages.  Everything else keeps the per-kernel path.
+// Scope: scalar models with a tridiagonal Jacobian (V == 1, P == 1), non-periodic, as many
+// stages as fit shared memory ((s + 2) vectors of the system: s <= 4 at N = 4096, every
+// tableau (s <= 6) up to N = 2048).  Everything else keeps the per-kernel path.
 #pragma once
 
 #if (TF_NVAR == 1) && (TF_P == 1)
 #define TF_HAS_SYSSTEP 1
 
 namespace tfk {
-
-constexpr int SYS_MAXK = 2;   // stage vectors kept in shared memory (s - 1 <= 2)
 
 // Exclusive prefix of every thread's element over the CTA (one tile, no look-back).
 // REV: the order runs from the last thread to the first (backward substitution); the
@@ -259,6 +258,8 @@ __device__ __forceinline__ void sys_border(const Geom& g, const Buf& b, int sys,
 
 // ---- one Rosenbrock stage: forward substitution of dt*F(U_i) + sum cfac_j k_j, border
 //      solve, backward substitution; k_i -> shared memory, or (last stage) U+ -> HBM.
+// ---- one Rosenbrock stage: forward substitution of dt*F(U_i) + sum cfac_j k_j, border
+//      solve, backward substitution; k_i -> shared memory, or (last stage) U+ -> HBM.
 template <int I, bool LAST>
 __device__ __forceinline__ void sys_stage(const Geom& g, const Buf& b, const Buf& lb, int sys,
                                           const TfStepDesc& sd, double dt, const double* cst,
@@ -467,13 +468,253 @@ __device__ __forceinline__ void sys_stage(const Geom& g, const Buf& b, const Buf
   (void)nwarps;
 }
 
+
+// Run-time stage index for the long tableaux (s > 3: ROS3PRL, RODASPR).
+// IMAX bounds the number of earlier stage vectors (compile time, loops unrolled and
+// predicated on the run-time stage index I <= IMAX): one instance serves every stage,
+// which keeps the kernel inside the instruction cache.
+template <int IMAX>
+__device__ __forceinline__ void sys_stage_rt(const int I, const bool LAST, const Geom& g, const Buf& b,
+                                          const Buf& lb, int sys, const TfStepDesc& sd, double dt,
+                                          const double* cst, SysShared& sh, const double* sU,
+                                          double* sK, double* sS, const double (&Lr)[C][BETA],
+                                          const double (&Ur)[C][BETA + 1], double& emax) {
+  const int T = blockDim.x;
+  const int TC = T * C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunk = threadIdx.x;
+  const int i0 = chunk * M;
+  const int sb = (warp * C) * 32 + lane;               // own chunk inside the system
+  const long long vs = vstride(g);
+  double alpha[IMAX > 0 ? IMAX : 1], cfac[IMAX > 0 ? IMAX : 1];
+#pragma unroll
+  for (int q = 0; q < IMAX; ++q) {
+    alpha[q] = q < I ? sd.alpha[I][q] : 0.0;
+    cfac[q] = q < I ? sd.cfac[I][q] : 0.0;
+  }
+  double y[C];
+  // ---------------------------------------------------------------- forward
+  {
+    // stage state U + ((alpha_0 k_0 + alpha_1 k_1) + ...), the reference's summation order
+    double own[C];
+#pragma unroll
+    for (int r = 0; r < C; ++r) {
+      double u = sU[sb + r * 32];
+      if (IMAX > 0 && I > 0) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < IMAX; ++q)
+          if (q < I) {
+            const double term = __dmul_rn(alpha[q], sK[q * TC + sb + r * 32]);
+            acc = (q == 0) ? term : __dadd_rn(acc, term);
+          }
+        u = __dadd_rn(u, acc);
+      }
+      own[r] = u;
+    }
+    const double* sH = sU;                              // where neighbours find the stage state
+    if (I > 0) {
+#pragma unroll
+      for (int r = 0; r < C; ++r) sS[sb + r * 32] = own[r];
+      sH = sS;
+    }
+    double win[NF][M + 2 * P];
+    const bool interior = i0 >= P && i0 + M + P <= g.N && P <= M && NH == 0 && chunk > 0 &&
+                          chunk < T - 1;
+    if (!interior) {                                    // edge chunks: clamped window (rare path)
+      Stage st;
+      st.nprev = I;
+#pragma unroll
+      for (int q = 0; q < MAXS; ++q) st.alpha[q] = (q < IMAX && q < I) ? sd.alpha[I][q < IMAX ? q : 0] : 0.0;
+      load_windows<M, -1>(win, i0, g, lb, sys, &st);
+    }
+    if (I > 0) __syncthreads();
+    if (interior) {
+#pragma unroll
+      for (int w = 0; w < M + 2 * P; ++w) {
+        const int rel = w - P;
+        const int dc = rel < 0 ? -1 : (rel >= M ? 1 : 0);
+        const int m = rel - dc * M;
+        const int t2 = (int)threadIdx.x + dc;
+        const int nb = ((t2 >> 5) * C) * 32 + (t2 & 31);
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          win[e][w] = (dc == 0) ? own[(m * V + e) < C ? (m * V + e) : 0] : sH[nb + (m * V + e) * 32];
+      }
+    }
+    RecState rs;
+    rs.init();
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      const int i = i0 + m;
+      double fe[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) fe[e] = 0.0;
+      {                                   // padding nodes too (finite fill, rhs zeroed below)
+        TfNodeIn in;
+        node_inputs<M>(in, win, m, i, g, b, sys);
+        tf_model_F<FD>(cst, in, fe);
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const int r = m * V + e;
+        double rhs = __dmul_rn(dt, fe[e]);
+#pragma unroll
+        for (int q = 0; q < IMAX; ++q)
+          if (q < I) rhs = __fma_rn(cfac[q], sK[q * TC + sb + r * 32], rhs);
+        rhs = (i < g.N) ? rhs : 0.0;
+        y[r] = rhs;
+        double coef[BETA];
+#pragma unroll
+        for (int q = 0; q < BETA; ++q) coef[q] = Lr[r][q];
+        rs.step(coef, rhs, 1.0);
+      }
+    }
+    Aff mine;
+    rs.to_map(mine);
+    const Aff pre = cta_scan<Aff, false>(mine, sh.scan);
+    double sv[BETA];
+#pragma unroll
+    for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
+#pragma unroll
+    for (int r = 0; r < C; ++r) {
+      double v = y[r];
+#pragma unroll
+      for (int q = 0; q < BETA; ++q) v -= Lr[r][q] * sv[q];
+#pragma unroll
+      for (int q = BETA - 1; q > 0; --q) sv[q] = sv[q - 1];
+      sv[0] = v;
+      y[r] = v;
+    }
+  }
+  // ------------------------------------------------- border solution x_b
+  const int r0 = chunk * C;
+  const int bot0 = g.nhat - NB;
+  const bool flagged = (r0 + C > g.nhat - NB && r0 < g.nhat + NB);
+  if (flagged) {
+#pragma unroll
+    for (int r = 0; r < C; ++r) {
+      const int gr = r0 + r;
+      if (gr >= bot0 && gr < g.nhat + NB) sh.ytail[gr - bot0] = y[r];
+    }
+  }
+  __syncthreads();
+  // border coupling of the few chunks that touch it: y <- y - W x_b on the fill rows,
+  // border rows <- x_b (applied once, ahead of both passes of the backward sweep)
+  if (flagged) {
+    double xb[NB], acc[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) acc[c] = 0.0;
+    for (int r = 0; r < NB; ++r) {
+      const double yr = sh.ytail[r];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) acc[c] = __fma_rn(sh.G[r * NB + c], yr, acc[c]);
+    }
+    double yb[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) yb[c] = __dsub_rn(sh.ytail[NB + c], acc[c]);
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) sacc = __fma_rn(sh.Sinv[r * NB + c], yb[c], sacc);
+      xb[r] = sacc;
+    }
+#pragma unroll
+    for (int r = 0; r < C; ++r) {
+      const int gr = r0 + r;
+      double yv = y[r];
+      if (gr >= bot0 && gr < g.nhat) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) yv = __fma_rn(-sh.W[(gr - bot0) * NB + c], xb[c], yv);
+      } else if (gr >= g.nhat && gr < g.nhat + NB) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) if (gr - g.nhat == c) yv = xb[c];
+      }
+      y[r] = yv;
+    }
+  }
+  // --------------------------------------------------------------- backward
+  Aff mine;
+  {
+    RecState rs;
+    rs.init();
+#pragma unroll
+    for (int r = C - 1; r >= 0; --r) {
+      double coef[BETA];
+#pragma unroll
+      for (int q = 0; q < BETA; ++q) coef[q] = Ur[r][q + 1];
+      rs.step(coef, y[r], Ur[r][0]);
+    }
+    rs.to_map(mine);
+  }
+  const Aff pre = cta_scan<Aff, true>(mine, sh.scan);
+  double sv[BETA];
+#pragma unroll
+  for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
+#pragma unroll
+  for (int r = C - 1; r >= 0; --r) {
+    double v = y[r];
+#pragma unroll
+    for (int q = 0; q < BETA; ++q) v -= Ur[r][q + 1] * sv[q];
+    v *= Ur[r][0];
+#pragma unroll
+    for (int q = BETA - 1; q > 0; --q) sv[q] = sv[q - 1];
+    sv[0] = v;
+    double k = v;
+    double kprev[IMAX > 0 ? IMAX : 1];
+#pragma unroll
+    for (int q = 0; q < IMAX; ++q)
+      if (q < I) {
+        kprev[q] = sK[q * TC + sb + r * 32];
+        k = __fma_rn(-cfac[q], kprev[q], k);
+      }
+    if (!LAST) {
+      sK[I * TC + sb + r * 32] = k;
+    } else {
+      // U + ((b0 k0 + b1 k1) + ...) in the reference's summation order (schemes.py:164-170)
+      double acc = 0.0, accp = 0.0;
+#pragma unroll
+      for (int q = 0; q <= IMAX; ++q)
+        if (q <= I) {
+          const double kq = (q < I) ? kprev[q < IMAX ? q : 0] : k;
+          const double t = __dmul_rn(sd.b[q], kq);
+          acc = (q == 0) ? t : __dadd_rn(acc, t);
+          const double tp = __dmul_rn(sd.bp[q], kq);
+          accp = (q == 0) ? tp : __dadd_rn(accp, tp);
+        }
+      const double un = __dadd_rn(sU[sb + r * 32], acc);
+      b.Un[sys * vs + sb + (long long)r * 32] = un;
+      if (sd.has_pred) {
+        const double e = fabs(__dsub_rn(un, __dadd_rn(un, accp)));
+        emax = (e > emax || e != e) ? e : emax;
+      }
+    }
+  }
+}
+
+// all stages of one step
+template <int IMAX>
+__device__ __forceinline__ void sys_stages(const Geom& g, const Buf& b, const Buf& lb, int sys,
+                                           const TfStepDesc& sd, double dt, const double* cst,
+                                           SysShared& sh, const double* sU, double* sK, double* sS,
+                                           const double (&Lr)[C][BETA],
+                                           const double (&Ur)[C][BETA + 1], double& emax) {
+#pragma unroll 1
+  for (int I = 0; I < sd.s; ++I) {
+    if (I > 0) __syncthreads();                         // k_{I-1} of the neighbours is in place
+    sys_stage_rt<IMAX>(I, I == sd.s - 1, g, b, lb, sys, sd, dt, cst, sh, sU, sK, sS, Lr, Ur, emax);
+  }
+}
+
 }  // namespace tfk
 
 // One CTA per system, persistent over the systems of the batch (grid = resident CTAs).
 // The next system's U is fetched by a bulk asynchronous copy (TMA) while the current
 // one is stepped.
-extern "C" __global__ void __launch_bounds__(tfk::NT, 1) tf_k_sysstep(tfk::Geom g, tfk::Buf b,
-                                                                      TfStepDesc sd) {
+template <bool LONG_TABLEAU>
+__device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf& b,
+                                             const TfStepDesc& sd) {
   using namespace tfk;
   extern __shared__ __align__(128) double dsm_sys[];
   double* dsm = dsm_sys;
@@ -481,8 +722,9 @@ extern "C" __global__ void __launch_bounds__(tfk::NT, 1) tf_k_sysstep(tfk::Geom 
   const int T = blockDim.x;
   const int TC = T * C;                                  // doubles per vector of one system
   double* sUb[2] = {dsm, dsm + TC};
-  double* sK = dsm + 2 * TC;                             // [SYS_MAXK][TC]
-  double* sS = dsm + (2 + SYS_MAXK) * TC;
+  const int nk = sd.s > 1 ? sd.s - 1 : 0;                // stage vectors kept in shared memory
+  double* sK = dsm + 2 * TC;                             // [nk][TC]
+  double* sS = dsm + (2 + nk) * TC;
   const long long vs = vstride(g);
   const unsigned bytes = (unsigned)(TC * sizeof(double));
   if (threadIdx.x == 0) { mbar_init(&sh.bar[0], 1); mbar_init(&sh.bar[1], 1); }
@@ -512,7 +754,7 @@ extern "C" __global__ void __launch_bounds__(tfk::NT, 1) tf_k_sysstep(tfk::Geom 
     Buf lb = b;                                          // U and k_j of this system: shared memory
     lb.U = const_cast<double*>(sU) - sys * vs;
 #pragma unroll
-    for (int q = 0; q < SYS_MAXK; ++q) lb.K[q] = sK + q * TC - sys * vs;
+    for (int q = 0; q < MAXS; ++q) lb.K[q] = (q < nk) ? sK + q * TC - sys * vs : nullptr;
     mbar_wait(&sh.bar[cur], phase[cur]);
     phase[cur] ^= 1u;
     __syncthreads();
@@ -522,17 +764,25 @@ extern "C" __global__ void __launch_bounds__(tfk::NT, 1) tf_k_sysstep(tfk::Geom 
     if (bad) atomicOr(b.status + sys, 1);
     sys_border(g, b, sys, a, sh, Lr, Ur);
     double emax = 0.0;
-    if (sd.s == 1) {
-      sys_stage<0, true>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
-    } else {
-      sys_stage<0, false>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
-      __syncthreads();
-      if (sd.s == 2) {
-        sys_stage<1, true>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
-      } else {
-        sys_stage<1, false>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
-        __syncthreads();
-        sys_stage<2, true>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+    if constexpr (LONG_TABLEAU) {
+      sys_stages<MAXS - 1>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+    } else {                                   // the common tableaux: stage index at compile time
+      switch (sd.s) {
+        case 1:
+          sys_stage<0, true>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+          break;
+        case 2:
+          sys_stage<0, false>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+          __syncthreads();
+          sys_stage<1, true>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+          break;
+        default:
+          sys_stage<0, false>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+          __syncthreads();
+          sys_stage<1, false>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+          __syncthreads();
+          sys_stage<2, true>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
+          break;
       }
     }
     // error estimate of the system
@@ -557,6 +807,17 @@ extern "C" __global__ void __launch_bounds__(tfk::NT, 1) tf_k_sysstep(tfk::Geom 
     sys = nxt;
     ++it;
   }
+}
+
+// s <= 3 (ROS2, ROS3PRw, Theta): stage index at compile time
+extern "C" __global__ void __launch_bounds__(tfk::NT, 1) tf_k_sysstep(tfk::Geom g, tfk::Buf b,
+                                                                      TfStepDesc sd) {
+  sysstep_body<false>(g, b, sd);
+}
+// s > 3 (ROS3PRL, RODASPR): one stage body with a run-time stage index
+extern "C" __global__ void __launch_bounds__(tfk::NT, 1) tf_k_sysstep_rt(tfk::Geom g, tfk::Buf b,
+                                                                         TfStepDesc sd) {
+  sysstep_body<true>(g, b, sd);
 }
 
 #endif  // V == 1 && P == 1

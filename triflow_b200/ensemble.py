@@ -59,7 +59,7 @@ class Ensemble:
     def set_fusion(self, enable):
         """System-resident stepping (one launch per step, state and factor kept on the SM)
         on / off; off selects the per-kernel pipeline (same algorithm, agrees to rounding)."""
-        _lib.check(_lib.lib().tf_state_set_fusion(self.state.h, int(bool(enable))))
+        _lib.check(_lib.lib().tf_state_set_fusion(self.state.h, 2 if enable == "rt" else int(bool(enable))))
 
     def upload(self, u):
         """``u``: (batch, N*nvar) in uflat layout."""
