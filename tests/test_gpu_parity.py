@@ -447,6 +447,43 @@ def test_system_resident_step_equals_kernel_pipeline(sname, kw, mname, N):
             assert np.allclose(out[alt][k], out[1][k], rtol=1e-9, atol=0, equal_nan=True)
 
 
+@pytest.mark.parametrize("batch,N", [(1500, 512), (450, 4096)])
+def test_system_resident_persistent_loop_many_systems_per_cta(batch, N):
+    """More systems than resident CTAs: every CTA steps several systems in turn, the next
+    system's U arriving by TMA while the current one is stepped (double buffer, mbarrier
+    phases).  Must equal the per-kernel pipeline member by member, also with members that a
+    per-member controller has switched off in between."""
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.ensemble import Ensemble
+    m = gmodel("advdiff")
+    c = W.ensemble(N, (np.arange(batch) * 21) % 32768)
+    rng = np.random.default_rng(11)
+    U0 = np.cos(2 * np.pi * 5 * c["x"]) + 0.2 * rng.standard_normal((batch, N))
+    out = []
+    for fused in (True, False):
+        ens = Ensemble(m, S.ROS3PRw(m, **FX), c["x"], dict(U=U0), c["pars"],
+                       hook=S.Dirichlet(U=(1.0, 0.0)), batch=batch)
+        ens.set_fusion(fused)
+        ens.step(c["dt"], 1)
+        ens.step(c["dt"], 5)
+        out.append(ens.download())
+    assert np.isfinite(out[0]).all()
+    scale = np.max(np.abs(out[1] - out[1].mean(axis=1, keepdims=True)), axis=1)
+    assert np.max(np.max(np.abs(out[0] - out[1]), axis=1) / scale) <= 1e-12
+    # adaptive per-member stepping on the same path (members finish at different times)
+    res = []
+    for fused in (True, False):
+        ens = Ensemble(m, S.ROS3PRw(m, tol=1e-2), c["x"], dict(U=U0[:300]),
+                       dict(k=c["pars"]["k"][:300], c=c["pars"]["c"][:300], periodic=False),
+                       hook=S.Dirichlet(U=(1.0, 0.0)), batch=300)
+        ens.set_fusion(fused)
+        nfs = ens.advance(0.5)
+        res.append((ens.download(), nfs.copy()))
+    assert np.array_equal(res[0][1], res[1][1])          # same accept / reject decisions
+    scale = np.max(np.abs(res[1][0] - res[1][0].mean(axis=1, keepdims=True)), axis=1)
+    assert np.max(np.max(np.abs(res[0][0] - res[1][0]), axis=1) / scale) <= 1e-10
+
+
 # ------------------------------------------- BASELINE.json full sizes vs the oracle
 @pytest.mark.parametrize("which,steps", [("burgers", 10), ("ks", 3), ("film", 2)])
 def test_full_size_configs_vs_oracle(which, steps):
