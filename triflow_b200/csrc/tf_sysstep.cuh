@@ -24,6 +24,13 @@
 #if (TF_NVAR == 1) && (TF_P == 1)
 #define TF_HAS_SYSSTEP 1
 
+
+#ifdef TF_TRACE
+#define SYS_CLK(ph) do { if (threadIdx.x == 0) { const long long t_ = clock64(); tf_trace[(blockIdx.x & 1023) * 32 + (ph)] += (unsigned long long)(t_ - sh.t0); sh.t0 = t_; } } while (0)
+#else
+#define SYS_CLK(ph) do { } while (0)
+#endif
+
 namespace tfk {
 
 // Exclusive prefix of every thread's element over the CTA (one tile, no look-back).
@@ -31,7 +38,7 @@ namespace tfk {
 // combine tree is the mirror image of the forward one, i.e. the tree the per-kernel
 // backward sweep builds with its reversed thread -> chunk assignment.
 template <class Mon, bool REV>
-__device__ __forceinline__ Mon cta_scan(const Mon& mine, double* smem) {
+__device__ __forceinline__ Mon cta_scan(const Mon& mine, double* smem, const int area) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int ml = REV ? 31 - lane : lane;               // position in scan order
   const int mw = REV ? nwarps - 1 - warp : warp;
@@ -44,7 +51,10 @@ __device__ __forceinline__ Mon cta_scan(const Mon& mine, double* smem) {
   }
   Mon excl = REV ? shfl_down(incl, 1) : shfl_up(incl, 1);
   excl = select(ml == 0, Mon::identity(), excl);
-  __syncthreads();                                     // scratch of the previous scan is consumed
+  // two scratch areas used in turn (factor 0, forward 1, backward 0, forward 1, ...): the
+  // barrier of the scan in between orders the reads of one use against the writes of the
+  // next one, so a scan costs one barrier
+  smem += area * (MAXW * KMAX);
   if (ml == 31) {
 #pragma unroll
     for (int k = 0; k < Mon::K; ++k) smem[mw * Mon::K + k] = incl.d[k];
@@ -55,14 +65,28 @@ __device__ __forceinline__ Mon cta_scan(const Mon& mine, double* smem) {
 #pragma unroll
     for (int k = 0; k < Mon::K; ++k) w.d[k] = smem[lane * Mon::K + k];
   }
-  const Mon wi = warp_scan(w, lane);
+  // warp totals: lanes >= nwarps hold the identity, levels d >= nwarps change nothing below
+  Mon wi = w;
+#pragma unroll
+  for (int d = 1; d < MAXW; d <<= 1) {
+    const Mon o = shfl_up(wi, d);
+    const Mon c = Mon::combine(o, wi);
+    wi = select(lane >= d, c, wi);
+  }
   Mon we = shfl_idx(wi, mw > 0 ? mw - 1 : 0);
   we = select(mw == 0, Mon::identity(), we);
-  return Mon::combine(Mon::combine(Mon::identity(), we), excl);
+  // (the pipeline's tile_scan composes an identity carry in front: exact, hence omitted)
+  return Mon::combine(we, excl);
 }
 
+constexpr int SYS_RPC = C + BETA;            // rows a chunk evaluates: its own + BETA of the next
+// chunk 0 + the chunks from the first one that reaches the last 2P nodes to the end of the
+// padding: at most 32 (a whole warp-block of padding) + ceil((2P + M + EX) / M) + 1 of them
+constexpr int SYS_EDGE_CHUNKS = 34 + (2 * P + M + EX + M - 1) / M;
+
 struct SysShared {
-  double scan[(MAXW + 1) * KMAX];
+  double scan[2 * MAXW * KMAX];
+  double edge[SYS_EDGE_CHUNKS * SYS_RPC * WB];  // band rows of the chunks that touch the domain ends
   double cst[NC2];
   double lnext[NT * BETA * BETA];      // L multipliers a chunk leaves on the next chunk's rows
   double tailL[NB * BETA];             // factor rows of the last NB interior unknowns
@@ -71,7 +95,62 @@ struct SysShared {
   double ytail[2 * NB];                // y of the last NB interior rows and of the border rows
   double err[MAXW];
   unsigned long long bar[2];
+  long long t0;                        // phase clock of the TF_TRACE build
 };
+
+// Band row of A = I - a*J for node i by the generic rule (domain ends, border, padding):
+// what node_row does for a chunk that is not "all regular", for ONE node.  Used by the
+// pre-pass below, where every such row gets its own thread instead of being walked by the
+// two threads that own the end chunks while 15 warps wait (measured: 22 % of the step).
+__device__ __noinline__ void sys_edge_row(int i, const Geom& g, const Buf& lb, int sys, double a,
+                                          const double* cst, double* out /* [WB] */) {
+  for (int d = 0; d < WB; ++d) out[d] = 0.0;
+  const int npad = g.nblk * 32 * M;
+  if (i >= npad) return;                          // beyond the system: no coupling
+  double jv[NNZ];
+  for (int kk = 0; kk < NNZ; ++kk) jv[kk] = 0.0;
+  if (i < g.N) {
+    TfNodeIn in;
+    const double* U = lb.U + sys * vstride(g);
+    for (int o = 0; o < TF_WW; ++o) {
+      const int j = map_node(i - P + o, g);
+      for (int e = 0; e < V; ++e) in.w[e][o] = U[vidx(j, e)];
+      for (int h = 0; h < NH; ++h)
+        in.w[V + h][o] = lb.H[(sys * (long long)NH + h) * hstride(g) + nidx(j)];
+    }
+#if TF_NNODEPAR > 0
+    for (int q = 0; q < TF_NNODEPAR; ++q)
+      in.np[q] = lb.NP[(sys * (long long)TF_NNODEPAR + q) * hstride(g) + nidx(i)];
+#endif
+#if TF_USES_X
+    in.x = lb.X[nidx(i)];
+#else
+    in.x = 0.0;
+#endif
+    tf_model_J<FD>(cst, in, jv);
+  }
+  if (i >= P && i < g.N - 2 * P) {
+    out[BETA] = 1.0;
+    for (int kk = 0; kk < NNZ; ++kk) {
+      const int d = tf_j_off(kk);
+      const double sv = __dmul_rn(a, jv[kk]);
+      out[BETA + d] = (d == 0) ? __dsub_rn(1.0, sv) : -sv;
+    }
+  } else {
+    assemble_special(i, g, jv, a, out, lb.btab + (long long)sys * 5 * NB * NB);
+  }
+}
+
+// first chunk (>= 1) that is not "all regular"; chunk 0 never is
+__device__ __forceinline__ int sys_first_tail_chunk(const Geom& g) {
+  constexpr int NODES = M + EX;
+  const int q = g.N - 2 * P - NODES;
+  const int c = q < 0 ? 1 : q / M + 1;
+  return c < 1 ? 1 : c;
+}
+__device__ __forceinline__ int sys_edge_slot(int chunk, int cfirst) {
+  return chunk == 0 ? 0 : 1 + (chunk - cfirst);
+}
 
 // ---- factorisation of the thread's rows into registers (factor_body_stream, V == 1)
 __device__ __forceinline__ void sys_factor(const Geom& g, const Buf& lb, int sys, double a,
@@ -85,16 +164,39 @@ __device__ __forceinline__ void sys_factor(const Geom& g, const Buf& lb, int sys
   double win[NF][NODES + 2 * P];
   Star mine = Star::identity();
   const bool allreg = i0 >= P && i0 + NODES <= g.N - 2 * P;
-  load_windows<NODES, 0>(win, i0, g, lb, sys, nullptr);
+  // pre-pass: the rows of the end chunks, one row per thread
+  const int cfirst = sys_first_tail_chunk(g);
+  const int nchunks = (int)blockDim.x;
+  const int nedge = 1 + (nchunks - cfirst);                   // chunk 0 + tail chunks
+  if (nedge > SYS_EDGE_CHUNKS) asm volatile("trap;");         // cannot happen (bound above)
+  for (int idx = threadIdx.x; idx < nedge * SYS_RPC; idx += blockDim.x) {
+    const int slot = idx / SYS_RPC, m = idx - slot * SYS_RPC;
+    const int c = slot == 0 ? 0 : cfirst + slot - 1;
+    sys_edge_row(c * M + m, g, lb, sys, a, cst, sh.edge + idx * WB);
+  }
+  __syncthreads();
+  SYS_CLK(5);                                            // edge-row pre-pass
+  const double* erow = sh.edge + sys_edge_slot(chunk, cfirst) * SYS_RPC * WB;
+  // the hot code only knows the regular rule; the generic one lives in sys_edge_row (keeping
+  // both in this function cost every thread 20 % through register allocation)
+  auto get_row = [&](double (&row)[WB], int m) {
+    if (!allreg) {
+#pragma unroll
+      for (int d = 0; d < WB; ++d) row[d] = erow[m * WB + d];
+    } else {
+      node_row<NODES>(row, win, m, i0, g, lb, sys, a, cst, true);
+    }
+  };
+  if (allreg) load_windows<NODES, 0>(win, i0, g, lb, sys, nullptr);
   {
     double cur[BETA][WB], nxt[BETA][WB];
 #pragma unroll
-    for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, lb, sys, a, cst, allreg);
+    for (int r = 0; r < BETA; ++r) get_row(cur[r], r);
 #pragma unroll
     for (int k = 0; k < NSB; ++k) {
 #pragma unroll
       for (int r = 0; r < BETA; ++r)
-        node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, lb, sys, a, cst, allreg);
+        get_row(nxt[r], (k + 1) * BETA + r);
       double Dh[BETA * BETA], Z[BETA * 2 * BETA], Rr[BETA * BETA];
 #pragma unroll
       for (int r = 0; r < BETA; ++r)
@@ -131,7 +233,9 @@ __device__ __forceinline__ void sys_factor(const Geom& g, const Buf& lb, int sys
     for (int q = 0; q < Star::K; ++q)
       if (!(fabs(mine.d[q]) < 1e300)) bad = 1;
   }
-  const Star pre = cta_scan<Star, false>(mine, sh.scan);
+  SYS_CLK(6);                                            // factor pass 1
+  const Star pre = cta_scan<Star, false>(mine, sh.scan, 0);
+  SYS_CLK(7);                                            // factor scan
   double X[BETA * BETA];
 #pragma unroll
   for (int q = 0; q < BETA * BETA; ++q) X[q] = pre.P()[q];
@@ -142,12 +246,12 @@ __device__ __forceinline__ void sys_factor(const Geom& g, const Buf& lb, int sys
     for (int q = 0; q < BETA; ++q) Lprev[r][q] = 0.0;
   double cur[BETA][WB], nxt[BETA][WB];
 #pragma unroll
-  for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, lb, sys, a, cst, allreg);
+  for (int r = 0; r < BETA; ++r) get_row(cur[r], r);
 #pragma unroll
   for (int k = 0; k < NSB; ++k) {
 #pragma unroll
     for (int r = 0; r < BETA; ++r)
-      node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, lb, sys, a, cst, allreg);
+      get_row(nxt[r], (k + 1) * BETA + r);
     double A2[2 * BETA][WB];
 #pragma unroll
     for (int r = 0; r < BETA; ++r)
@@ -343,7 +447,9 @@ __device__ __forceinline__ void sys_stage(const Geom& g, const Buf& b, const Buf
     }
     Aff mine;
     rs.to_map(mine);
-    const Aff pre = cta_scan<Aff, false>(mine, sh.scan);
+    SYS_CLK(8);                                          // stage: state, halo, F, first pass
+    const Aff pre = cta_scan<Aff, false>(mine, sh.scan, 1);
+    SYS_CLK(9);                                          // forward scan
     double sv[BETA];
 #pragma unroll
     for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
@@ -425,7 +531,9 @@ __device__ __forceinline__ void sys_stage(const Geom& g, const Buf& b, const Buf
     }
     rs.to_map(mine);
   }
-  const Aff pre = cta_scan<Aff, true>(mine, sh.scan);
+  SYS_CLK(10);                                           // fwd pass 2, border, bwd pass 1
+  const Aff pre = cta_scan<Aff, true>(mine, sh.scan, 0);
+  SYS_CLK(11);                                           // backward scan
   double sv[BETA];
 #pragma unroll
   for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
@@ -572,7 +680,7 @@ __device__ __forceinline__ void sys_stage_rt(const int I, const bool LAST, const
     }
     Aff mine;
     rs.to_map(mine);
-    const Aff pre = cta_scan<Aff, false>(mine, sh.scan);
+    const Aff pre = cta_scan<Aff, false>(mine, sh.scan, 1);
     double sv[BETA];
 #pragma unroll
     for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
@@ -648,7 +756,7 @@ __device__ __forceinline__ void sys_stage_rt(const int I, const bool LAST, const
     }
     rs.to_map(mine);
   }
-  const Aff pre = cta_scan<Aff, true>(mine, sh.scan);
+  const Aff pre = cta_scan<Aff, true>(mine, sh.scan, 0);
   double sv[BETA];
 #pragma unroll
   for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
@@ -731,6 +839,9 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
   __syncthreads();
   unsigned phase[2] = {0u, 0u};
   int it = 0;
+#ifdef TF_TRACE
+  if (threadIdx.x == 0) sh.t0 = clock64();
+#endif
   auto is_active = [&](int s) { return b.active == nullptr || b.active[s] != 0; };
   // first system of this CTA
   int sys = blockIdx.x;
@@ -760,9 +871,12 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
     __syncthreads();
     double Lr[C][BETA], Ur[C][BETA + 1];
     int bad = 0;
+    SYS_CLK(0);                                          // wait for U (TMA) + constants
     sys_factor(g, lb, sys, a, sh.cst, sh, Lr, Ur, bad);
+    SYS_CLK(1);
     if (bad) atomicOr(b.status + sys, 1);
     sys_border(g, b, sys, a, sh, Lr, Ur);
+    SYS_CLK(2);
     double emax = 0.0;
     if constexpr (LONG_TABLEAU) {
       sys_stages<MAXS - 1>(g, b, lb, sys, sd, dt, sh.cst, sh, sU, sK, sS, Lr, Ur, emax);
@@ -785,6 +899,7 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
           break;
       }
     }
+    SYS_CLK(3);                                          // all stages
     // error estimate of the system
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (sd.has_pred) {
@@ -796,6 +911,7 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
       if (lane == 0) sh.err[warp] = emax;
     }
     __syncthreads();                                     // releases sU[cur], sK, sS, sh.*
+    SYS_CLK(4);
     if (threadIdx.x == 0) {
       double e = 0.0;
       if (sd.has_pred) {
