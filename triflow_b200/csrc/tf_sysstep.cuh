@@ -94,51 +94,107 @@ struct SysShared {
   double W[NB * NB], G[NB * NB], Sinv[NB * NB];
   double ytail[2 * NB];                // y of the last NB interior rows and of the border rows
   double err[MAXW];
+  double btab[5 * NB * NB];            // raw J of the border couplings (assemble_special)
   unsigned long long bar[2];
   long long t0;                        // phase clock of the TF_TRACE build
 };
 
 // Band row of A = I - a*J for node i by the generic rule (domain ends, border, padding):
-// what node_row does for a chunk that is not "all regular", for ONE node.  Used by the
+// what node_row + assemble_special do for a chunk that is not "all regular", for ONE node and
+// for V == 1, with the row in registers and the border tables in shared memory (the generic
+// assemble_special walks local / generic memory: ~3800 cycles per row, measured).  Same
+// operations in the same order (the entries of one row are summed in kk order).  Used by the
 // pre-pass below, where every such row gets its own thread instead of being walked by the
-// two threads that own the end chunks while 15 warps wait (measured: 22 % of the step).
-__device__ __noinline__ void sys_edge_row(int i, const Geom& g, const Buf& lb, int sys, double a,
-                                          const double* cst, double* out /* [WB] */) {
-  for (int d = 0; d < WB; ++d) out[d] = 0.0;
+// two threads that own the end chunks while 15 warps wait.
+__device__ __noinline__ void sys_edge_row(int i, const Geom& g, const double* sU, const Buf& lb,
+                                          int sys, double a, const double* cst,
+                                          double* out /* [WB] */, double* btab /* shared */,
+                                          bool tables /* this call owns the node's table rows */) {
+  static_assert(V == 1, "rows == nodes");
+  double rows[WB];
+#pragma unroll
+  for (int d = 0; d < WB; ++d) rows[d] = 0.0;
   const int npad = g.nblk * 32 * M;
-  if (i >= npad) return;                          // beyond the system: no coupling
-  double jv[NNZ];
-  for (int kk = 0; kk < NNZ; ++kk) jv[kk] = 0.0;
-  if (i < g.N) {
-    TfNodeIn in;
-    const double* U = lb.U + sys * vstride(g);
-    for (int o = 0; o < TF_WW; ++o) {
-      const int j = map_node(i - P + o, g);
-      for (int e = 0; e < V; ++e) in.w[e][o] = U[vidx(j, e)];
-      for (int h = 0; h < NH; ++h)
-        in.w[V + h][o] = lb.H[(sys * (long long)NH + h) * hstride(g) + nidx(j)];
-    }
+  const int nint = g.N - P;                     // interior nodes
+  if (i < npad) {
+    double jv[NNZ];
+#pragma unroll
+    for (int kk = 0; kk < NNZ; ++kk) jv[kk] = 0.0;
+    if (i < g.N) {
+      TfNodeIn in;
+#pragma unroll
+      for (int o = 0; o < TF_WW; ++o) {
+        const int j = map_node(i - P + o, g);
+        in.w[0][o] = sU[(int)vidx(j, 0)];
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+          in.w[V + h][o] = lb.H[(sys * (long long)NH + h) * hstride(g) + nidx(j)];
+      }
 #if TF_NNODEPAR > 0
-    for (int q = 0; q < TF_NNODEPAR; ++q)
-      in.np[q] = lb.NP[(sys * (long long)TF_NNODEPAR + q) * hstride(g) + nidx(i)];
+#pragma unroll
+      for (int q = 0; q < TF_NNODEPAR; ++q)
+        in.np[q] = lb.NP[(sys * (long long)TF_NNODEPAR + q) * hstride(g) + nidx(i)];
 #endif
 #if TF_USES_X
-    in.x = lb.X[nidx(i)];
+      in.x = lb.X[nidx(i)];
 #else
-    in.x = 0.0;
+      in.x = 0.0;
 #endif
-    tf_model_J<FD>(cst, in, jv);
-  }
-  if (i >= P && i < g.N - 2 * P) {
-    out[BETA] = 1.0;
-    for (int kk = 0; kk < NNZ; ++kk) {
-      const int d = tf_j_off(kk);
-      const double sv = __dmul_rn(a, jv[kk]);
-      out[BETA + d] = (d == 0) ? __dsub_rn(1.0, sv) : -sv;
+      tf_model_J<FD>(cst, in, jv);
     }
-  } else {
-    assemble_special(i, g, jv, a, out, lb.btab + (long long)sys * 5 * NB * NB);
+    if (i >= P && i < g.N - 2 * P) {            // regular rule
+      rows[BETA] = 1.0;
+#pragma unroll
+      for (int kk = 0; kk < NNZ; ++kk) {
+        const int d = tf_j_off(kk);
+        const double sv = __dmul_rn(a, jv[kk]);
+        rows[BETA + d] = (d == 0) ? __dsub_rn(1.0, sv) : -sv;
+      }
+    } else if (i >= nint) {                     // border row or padding: identity in the band
+      rows[BETA] = 1.0;
+      if (i < g.N && tables) {
+        double* Ft = btab + 2 * NB * NB;
+        double* Fb = btab + 3 * NB * NB;
+        double* Ab = btab + 4 * NB * NB;
+        const int r = i - nint;
+        for (int c = 0; c < NB; ++c) { Ft[r * NB + c] = 0.0; Fb[r * NB + c] = 0.0; Ab[r * NB + c] = 0.0; }
+#pragma unroll
+        for (int kk = 0; kk < NNZ; ++kk) {
+          const int j = map_node(i + tf_j_off(kk), g);
+          if (j >= nint) Ab[r * NB + (j - nint)] += jv[kk];
+          else if (j < P) Ft[r * NB + j] += jv[kk];
+          else Fb[r * NB + (j - (g.N - 2 * P))] += jv[kk];
+        }
+      }
+    } else {                                    // first P / last interior rows
+      double* Et = btab;
+      double* Eb = btab + NB * NB;
+      const bool top = i < P;
+      if (tables) {
+        if (top) for (int c = 0; c < NB; ++c) Et[i * NB + c] = 0.0;
+        else for (int c = 0; c < NB; ++c) Eb[(i - (g.N - 2 * P)) * NB + c] = 0.0;
+      }
+#pragma unroll
+      for (int kk = 0; kk < NNZ; ++kk) {
+        const int j = map_node(i + tf_j_off(kk), g);
+        if (j < nint) {
+          const int d = j - i;
+#pragma unroll
+          for (int dd = -BETA; dd <= BETA; ++dd) rows[BETA + dd] += (d == dd) ? jv[kk] : 0.0;
+        } else if (tables) {
+          if (top) Et[i * NB + (j - nint)] += jv[kk];
+          else Eb[(i - (g.N - 2 * P)) * NB + (j - nint)] += jv[kk];
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < WB; ++d) {
+        const double sv = __dmul_rn(a, rows[d]);
+        rows[d] = (d == BETA) ? __dsub_rn(1.0, sv) : -sv;
+      }
+    }
   }
+#pragma unroll
+  for (int d = 0; d < WB; ++d) out[d] = rows[d];
 }
 
 // first chunk (>= 1) that is not "all regular"; chunk 0 never is
@@ -169,10 +225,17 @@ __device__ __forceinline__ void sys_factor(const Geom& g, const Buf& lb, int sys
   const int nchunks = (int)blockDim.x;
   const int nedge = 1 + (nchunks - cfirst);                   // chunk 0 + tail chunks
   if (nedge > SYS_EDGE_CHUNKS) asm volatile("trap;");         // cannot happen (bound above)
-  for (int idx = threadIdx.x; idx < nedge * SYS_RPC; idx += blockDim.x) {
+  // rows are dealt to the warps first (row k -> warp k mod nwarps): the row kinds (regular,
+  // top, bottom, border, padding) take different branches, which would serialise inside a warp
+  const int nwarps_e = (int)blockDim.x >> 5;
+  for (int idx = (int)(threadIdx.x & 31) * nwarps_e + (int)(threadIdx.x >> 5); idx < nedge * SYS_RPC;
+       idx += blockDim.x) {
     const int slot = idx / SYS_RPC, m = idx - slot * SYS_RPC;
     const int c = slot == 0 ? 0 : cfirst + slot - 1;
-    sys_edge_row(c * M + m, g, lb, sys, a, cst, sh.edge + idx * WB);
+    // a node shared by two end chunks (row m >= M of one = row m - M of the next) is evaluated
+    // twice; only its owner writes the border tables
+    sys_edge_row(c * M + m, g, lb.U + sys * vstride(g), lb, sys, a, cst, sh.edge + idx * WB, sh.btab,
+                 m < M || slot == 0 && cfirst > 1);
   }
   __syncthreads();
   SYS_CLK(5);                                            // edge-row pre-pass
@@ -320,7 +383,7 @@ __device__ __forceinline__ void sys_border(const Geom& g, const Buf& b, int sys,
     }
   }
   __syncthreads();                       // also orders the btab rows written by node_row
-  const double* bt = b.btab + (long long)sys * 5 * NB * NB;
+  const double* bt = sh.btab;
   if (threadIdx.x < 2 * NB) {
     const bool isW = threadIdx.x < NB;
     const int c = isW ? threadIdx.x : threadIdx.x - NB;
@@ -397,12 +460,20 @@ __device__ __forceinline__ void sys_stage(const Geom& g, const Buf& b, const Buf
       sH = sS;
     }
     double win[NF][M + 2 * P];
-    const bool interior = i0 >= P && i0 + M + P <= g.N && P <= M && NH == 0 && chunk > 0 &&
-                          chunk < T - 1;
-    if (!interior) {
-      Buf eb = lb;                                      // edge chunks: clamped window
-      eb.U = const_cast<double*>(sU) - sys * vs;
-      load_windows<M, I>(win, i0, g, eb, sys, &st);
+    // Stencil windows.  Without helper fields every chunk takes its halo from the neighbouring
+    // threads' values in shared memory; the chunks at the ends of the (non-periodic) domain
+    // then replace what lies outside by the end values (edge replication, map_node).  The
+    // generic window loader stays out of this function: it cost the end threads ~2000 cycles
+    // per stage while everybody else waited at the scan barrier.
+    constexpr bool FASTWIN = (NH == 0) && (P <= M);
+    bool interior = true;
+    if (!FASTWIN) {
+      interior = i0 >= P && i0 + M + P <= g.N && P <= M && NH == 0 && chunk > 0 && chunk < T - 1;
+      if (!interior) {
+        Buf eb = lb;                                    // edge chunks: clamped window
+        eb.U = const_cast<double*>(sU) - sys * vs;
+        load_windows<M, I>(win, i0, g, eb, sys, &st);
+      }
     }
     if (I > 0) __syncthreads();
     if (interior) {
@@ -415,7 +486,19 @@ __device__ __forceinline__ void sys_stage(const Geom& g, const Buf& b, const Buf
         const int nb = ((t2 >> 5) * C) * 32 + (t2 & 31);
 #pragma unroll
         for (int e = 0; e < V; ++e)
-          win[e][w] = (dc == 0) ? own[(m * V + e) < C ? (m * V + e) : 0] : sH[nb + (m * V + e) * 32];
+          win[e][w] = (dc == 0) ? own[(m * V + e) < C ? (m * V + e) : 0]
+                                : ((t2 >= 0 && t2 < T) ? sH[nb + (m * V + e) * 32] : 0.0);
+      }
+      if (FASTWIN && (i0 < P || i0 + M + P > g.N)) {      // domain ends and padding
+#pragma unroll
+        for (int w = 0; w < M + 2 * P; ++w) {
+          const int j = i0 - P + w;
+          if (j < 0 || j >= g.N) {
+            const int jc = j < 0 ? 0 : g.N - 1;
+#pragma unroll
+            for (int e = 0; e < V; ++e) win[e][w] = sH[(int)vidx(jc, e)];
+          }
+        }
       }
     }
     RecState rs;
@@ -835,6 +918,7 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
   double* sS = dsm + (2 + nk) * TC;
   const long long vs = vstride(g);
   const unsigned bytes = (unsigned)(TC * sizeof(double));
+  constexpr int CST_PT = (NC2 + 31) / 32;                // constants per thread (T >= 32)
   if (threadIdx.x == 0) { mbar_init(&sh.bar[0], 1); mbar_init(&sh.bar[1], 1); }
   __syncthreads();
   unsigned phase[2] = {0u, 0u};
@@ -860,7 +944,16 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
     }
     const double a = (b.asys != nullptr) ? b.asys[sys] : sd.a;
     const double dt = (b.dtsys != nullptr) ? b.dtsys[sys] : sd.dt;
-    for (int k = threadIdx.x; k < NC2; k += T) sh.cst[k] = b.cst[(long long)sys * NC2 + k];
+    if (it == 0) {
+      for (int k = threadIdx.x; k < NC2; k += T) sh.cst[k] = b.cst[(long long)sys * NC2 + k];
+    }
+    // constants of the next system: loaded now, stored behind the barrier that ends this one
+    double cst_next[CST_PT];
+#pragma unroll
+    for (int k = 0; k < CST_PT; ++k) {
+      const int idx = threadIdx.x + k * T;
+      cst_next[k] = (nxt < g.batch && idx < NC2) ? b.cst[(long long)nxt * NC2 + idx] : 0.0;
+    }
     const double* sU = sUb[cur];
     Buf lb = b;                                          // U and k_j of this system: shared memory
     lb.U = const_cast<double*>(sU) - sys * vs;
@@ -911,14 +1004,23 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
       if (lane == 0) sh.err[warp] = emax;
     }
     __syncthreads();                                     // releases sU[cur], sK, sS, sh.*
+#pragma unroll
+    for (int k = 0; k < CST_PT; ++k) {
+      const int idx = threadIdx.x + k * T;
+      if (nxt < g.batch && idx < NC2) sh.cst[idx] = cst_next[k];
+    }
     SYS_CLK(4);
-    if (threadIdx.x == 0) {
+    if (warp == 0) {                                     // max over the warps (NaN sticks)
       double e = 0.0;
       if (sd.has_pred) {
-        e = sh.err[0];
-        for (int w = 1; w < (T >> 5); ++w) e = (sh.err[w] > e || sh.err[w] != sh.err[w]) ? sh.err[w] : e;
+        e = (lane < (T >> 5)) ? sh.err[lane] : 0.0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          const double o = __shfl_xor_sync(0xffffffffu, e, d);
+          e = (o > e || o != o) ? o : e;
+        }
       }
-      b.err[sys] = e;
+      if (lane == 0) b.err[sys] = e;
     }
     sys = nxt;
     ++it;
