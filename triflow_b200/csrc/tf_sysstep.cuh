@@ -8,8 +8,10 @@
 // the banded factor and the forward-substitution result live in the registers of the
 // thread that owns the rows, and a step reads U once and writes U+ once (16 bytes per
 // node instead of 224 for ROS3PRw).  The algorithm is the one of the per-kernel path
-// (same chunking, same scan trees); the two differ only in where ptxas contracts a*b+c
-// into an FMA (identical bits when built with -fmad=false), tests compare them to 1e-12.
+// (same chunking, same two-pass chunk scans) with one simplification: a non-periodic system
+// is purely banded, so the border block the pipeline shares with periodic systems (last P
+// nodes ordered last, Schur complement, x_b) does not exist here.  The two paths agree to
+// rounding; tests compare them to 1e-12.
 //
 // Replaces, in one launch (reference file:line): compute_J_numpy + I - gamma*dt*J +
 // factorized (compilers.py:292-332, schemes.py:146-149), the s stages of
@@ -80,7 +82,7 @@ __device__ __forceinline__ Mon cta_scan(const Mon& mine, double* smem, const int
 }
 
 constexpr int SYS_RPC = C + BETA;            // rows a chunk evaluates: its own + BETA of the next
-// chunk 0 + the chunks from the first one that reaches the last 2P nodes to the end of the
+// chunk 0 + the chunks from the first one that reaches the last P nodes to the end of the
 // padding: at most 32 (a whole warp-block of padding) + ceil((2P + M + EX) / M) + 1 of them
 constexpr int SYS_EDGE_CHUNKS = 34 + (2 * P + M + EX + M - 1) / M;
 
@@ -89,108 +91,61 @@ struct SysShared {
   double edge[SYS_EDGE_CHUNKS * SYS_RPC * WB];  // band rows of the chunks that touch the domain ends
   double cst[NC2];
   double lnext[NT * BETA * BETA];      // L multipliers a chunk leaves on the next chunk's rows
-  double tailL[NB * BETA];             // factor rows of the last NB interior unknowns
-  double tailU[NB * (BETA + 1)];
-  double W[NB * NB], G[NB * NB], Sinv[NB * NB];
-  double ytail[2 * NB];                // y of the last NB interior rows and of the border rows
   double err[MAXW];
-  double btab[5 * NB * NB];            // raw J of the border couplings (assemble_special)
   unsigned long long bar[2];
   long long t0;                        // phase clock of the TF_TRACE build
 };
 
-// Band row of A = I - a*J for node i by the generic rule (domain ends, border, padding):
-// what node_row + assemble_special do for a chunk that is not "all regular", for ONE node and
-// for V == 1, with the row in registers and the border tables in shared memory (the generic
-// assemble_special walks local / generic memory: ~3800 cycles per row, measured).  Same
-// operations in the same order (the entries of one row are summed in kk order).  Used by the
-// pre-pass below, where every such row gets its own thread instead of being walked by the
+// Band row of A = I - a*J for node i at the ends of the domain, for ONE node and V == 1.
+// A non-periodic system is purely banded: a stencil neighbour outside the domain is the end
+// node itself (edge replication, compilers.py:261-264,311-319), so its Jacobian entry is
+// added onto the column of the end node -- inside the band.  The per-kernel pipeline orders
+// the last P nodes last and eliminates them through a border block because it shares that
+// code with periodic systems; here no border block, no Schur complement and no x_b exist.
+// Entries of one row are summed in kk order, like the reference's COO -> CSC duplicate sum.
+// Every such row gets its own thread in the pre-pass below instead of being walked by the
 // two threads that own the end chunks while 15 warps wait.
 __device__ __noinline__ void sys_edge_row(int i, const Geom& g, const double* sU, const Buf& lb,
                                           int sys, double a, const double* cst,
-                                          double* out /* [WB] */, double* btab /* shared */,
-                                          bool tables /* this call owns the node's table rows */) {
+                                          double* out /* [WB] */) {
   static_assert(V == 1, "rows == nodes");
   double rows[WB];
 #pragma unroll
   for (int d = 0; d < WB; ++d) rows[d] = 0.0;
   const int npad = g.nblk * 32 * M;
-  const int nint = g.N - P;                     // interior nodes
-  if (i < npad) {
+  if (i >= g.N && i < npad) rows[BETA] = 1.0;   // padding: identity (beyond npad: no row)
+  if (i < g.N) {
     double jv[NNZ];
+    TfNodeIn in;
 #pragma unroll
-    for (int kk = 0; kk < NNZ; ++kk) jv[kk] = 0.0;
-    if (i < g.N) {
-      TfNodeIn in;
+    for (int o = 0; o < TF_WW; ++o) {
+      const int j = map_node(i - P + o, g);
+      in.w[0][o] = sU[(int)vidx(j, 0)];
 #pragma unroll
-      for (int o = 0; o < TF_WW; ++o) {
-        const int j = map_node(i - P + o, g);
-        in.w[0][o] = sU[(int)vidx(j, 0)];
-#pragma unroll
-        for (int h = 0; h < NH; ++h)
-          in.w[V + h][o] = lb.H[(sys * (long long)NH + h) * hstride(g) + nidx(j)];
-      }
+      for (int h = 0; h < NH; ++h)
+        in.w[V + h][o] = lb.H[(sys * (long long)NH + h) * hstride(g) + nidx(j)];
+    }
 #if TF_NNODEPAR > 0
 #pragma unroll
-      for (int q = 0; q < TF_NNODEPAR; ++q)
-        in.np[q] = lb.NP[(sys * (long long)TF_NNODEPAR + q) * hstride(g) + nidx(i)];
+    for (int q = 0; q < TF_NNODEPAR; ++q)
+      in.np[q] = lb.NP[(sys * (long long)TF_NNODEPAR + q) * hstride(g) + nidx(i)];
 #endif
 #if TF_USES_X
-      in.x = lb.X[nidx(i)];
+    in.x = lb.X[nidx(i)];
 #else
-      in.x = 0.0;
+    in.x = 0.0;
 #endif
-      tf_model_J<FD>(cst, in, jv);
+    tf_model_J<FD>(cst, in, jv);
+#pragma unroll
+    for (int kk = 0; kk < NNZ; ++kk) {
+      const int d = map_node(i + tf_j_off(kk), g) - i;       // clamped neighbour, |d| <= P
+#pragma unroll
+      for (int dd = -BETA; dd <= BETA; ++dd) rows[BETA + dd] += (d == dd) ? jv[kk] : 0.0;
     }
-    if (i >= P && i < g.N - 2 * P) {            // regular rule
-      rows[BETA] = 1.0;
 #pragma unroll
-      for (int kk = 0; kk < NNZ; ++kk) {
-        const int d = tf_j_off(kk);
-        const double sv = __dmul_rn(a, jv[kk]);
-        rows[BETA + d] = (d == 0) ? __dsub_rn(1.0, sv) : -sv;
-      }
-    } else if (i >= nint) {                     // border row or padding: identity in the band
-      rows[BETA] = 1.0;
-      if (i < g.N && tables) {
-        double* Ft = btab + 2 * NB * NB;
-        double* Fb = btab + 3 * NB * NB;
-        double* Ab = btab + 4 * NB * NB;
-        const int r = i - nint;
-        for (int c = 0; c < NB; ++c) { Ft[r * NB + c] = 0.0; Fb[r * NB + c] = 0.0; Ab[r * NB + c] = 0.0; }
-#pragma unroll
-        for (int kk = 0; kk < NNZ; ++kk) {
-          const int j = map_node(i + tf_j_off(kk), g);
-          if (j >= nint) Ab[r * NB + (j - nint)] += jv[kk];
-          else if (j < P) Ft[r * NB + j] += jv[kk];
-          else Fb[r * NB + (j - (g.N - 2 * P))] += jv[kk];
-        }
-      }
-    } else {                                    // first P / last interior rows
-      double* Et = btab;
-      double* Eb = btab + NB * NB;
-      const bool top = i < P;
-      if (tables) {
-        if (top) for (int c = 0; c < NB; ++c) Et[i * NB + c] = 0.0;
-        else for (int c = 0; c < NB; ++c) Eb[(i - (g.N - 2 * P)) * NB + c] = 0.0;
-      }
-#pragma unroll
-      for (int kk = 0; kk < NNZ; ++kk) {
-        const int j = map_node(i + tf_j_off(kk), g);
-        if (j < nint) {
-          const int d = j - i;
-#pragma unroll
-          for (int dd = -BETA; dd <= BETA; ++dd) rows[BETA + dd] += (d == dd) ? jv[kk] : 0.0;
-        } else if (tables) {
-          if (top) Et[i * NB + (j - nint)] += jv[kk];
-          else Eb[(i - (g.N - 2 * P)) * NB + (j - nint)] += jv[kk];
-        }
-      }
-#pragma unroll
-      for (int d = 0; d < WB; ++d) {
-        const double sv = __dmul_rn(a, rows[d]);
-        rows[d] = (d == BETA) ? __dsub_rn(1.0, sv) : -sv;
-      }
+    for (int d = 0; d < WB; ++d) {
+      const double sv = __dmul_rn(a, rows[d]);
+      rows[d] = (d == BETA) ? __dsub_rn(1.0, sv) : -sv;
     }
   }
 #pragma unroll
@@ -200,7 +155,7 @@ __device__ __noinline__ void sys_edge_row(int i, const Geom& g, const double* sU
 // first chunk (>= 1) that is not "all regular"; chunk 0 never is
 __device__ __forceinline__ int sys_first_tail_chunk(const Geom& g) {
   constexpr int NODES = M + EX;
-  const int q = g.N - 2 * P - NODES;
+  const int q = g.N - P - NODES;
   const int c = q < 0 ? 1 : q / M + 1;
   return c < 1 ? 1 : c;
 }
@@ -219,7 +174,7 @@ __device__ __forceinline__ void sys_factor(const Geom& g, const Buf& lb, int sys
   const int i0 = chunk * M;
   double win[NF][NODES + 2 * P];
   Star mine = Star::identity();
-  const bool allreg = i0 >= P && i0 + NODES <= g.N - 2 * P;
+  const bool allreg = i0 >= P && i0 + NODES <= g.N - P;   // no stencil leaves the domain
   // pre-pass: the rows of the end chunks, one row per thread
   const int cfirst = sys_first_tail_chunk(g);
   const int nchunks = (int)blockDim.x;
@@ -232,10 +187,7 @@ __device__ __forceinline__ void sys_factor(const Geom& g, const Buf& lb, int sys
        idx += blockDim.x) {
     const int slot = idx / SYS_RPC, m = idx - slot * SYS_RPC;
     const int c = slot == 0 ? 0 : cfirst + slot - 1;
-    // a node shared by two end chunks (row m >= M of one = row m - M of the next) is evaluated
-    // twice; only its owner writes the border tables
-    sys_edge_row(c * M + m, g, lb.U + sys * vstride(g), lb, sys, a, cst, sh.edge + idx * WB, sh.btab,
-                 m < M || slot == 0 && cfirst > 1);
+    sys_edge_row(c * M + m, g, lb.U + sys * vstride(g), lb, sys, a, cst, sh.edge + idx * WB);
   }
   __syncthreads();
   SYS_CLK(5);                                            // edge-row pre-pass
@@ -363,66 +315,6 @@ __device__ __forceinline__ void sys_factor(const Geom& g, const Buf& lb, int sys
   }
 }
 
-// ---- border block of a non-periodic system: the natural coupling of the last NB
-//      interior rows to the border unknowns (bottom part of tf_k_border_fill)
-__device__ __forceinline__ void sys_border(const Geom& g, const Buf& b, int sys, double a,
-                                           SysShared& sh, const double (&Lr)[C][BETA],
-                                           const double (&Ur)[C][BETA + 1]) {
-  const int bot0 = g.nhat - NB;
-  const int r0 = threadIdx.x * C;
-  if (r0 + C > bot0 && r0 < g.nhat) {
-#pragma unroll
-    for (int r = 0; r < C; ++r) {
-      const int gr = r0 + r;
-      if (gr >= bot0 && gr < g.nhat) {
-#pragma unroll
-        for (int q = 0; q < BETA; ++q) sh.tailL[(gr - bot0) * BETA + q] = Lr[r][q];
-#pragma unroll
-        for (int q = 0; q <= BETA; ++q) sh.tailU[(gr - bot0) * (BETA + 1) + q] = Ur[r][q];
-      }
-    }
-  }
-  __syncthreads();                       // also orders the btab rows written by node_row
-  const double* bt = sh.btab;
-  if (threadIdx.x < 2 * NB) {
-    const bool isW = threadIdx.x < NB;
-    const int c = isW ? threadIdx.x : threadIdx.x - NB;
-    double loc[NB];
-    for (int j = 0; j < NB; ++j) {
-      double v = -(a * (isW ? bt[1 * NB * NB + j * NB + c] : bt[3 * NB * NB + c * NB + j]));
-      for (int q = 1; q <= BETA; ++q) {
-        const int jj = j - q;
-        if (jj < 0) break;
-        const double coef = isW ? sh.tailL[j * BETA + q - 1]
-                                : sh.tailU[(j - q) * (BETA + 1) + q] * sh.tailU[(j - q) * (BETA + 1)];
-        v -= coef * loc[jj];
-      }
-      loc[j] = v;
-      const double out = isW ? v : v * sh.tailU[j * (BETA + 1)];
-      (isW ? sh.W : sh.G)[j * NB + c] = 0.0 + out;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double S[NB * NB], I[NB * NB];
-    for (int i = 0; i < NB; ++i)
-      for (int j = 0; j < NB; ++j) {
-        double v = 0.0;
-        for (int r = 0; r < NB; ++r) v = __fma_rn(sh.G[r * NB + i], sh.W[r * NB + j], v);
-        S[i * NB + j] = __dsub_rn(__fma_rn(-a, bt[4 * NB * NB + i * NB + j], (i == j) ? 1.0 : 0.0), v);
-        I[i * NB + j] = (i == j) ? 1.0 : 0.0;
-      }
-    tfb::solve_inplace<NB, NB>(S, I);
-    bool bad = false;
-    for (int k = 0; k < NB * NB; ++k) {
-      sh.Sinv[k] = I[k];
-      if (!(fabs(I[k]) < 1e300)) bad = true;
-    }
-    if (bad) atomicOr(b.status + sys, 2);
-  }
-  __syncthreads();
-}
-
 // ---- one Rosenbrock stage: forward substitution of dt*F(U_i) + sum cfac_j k_j, border
 //      solve, backward substitution; k_i -> shared memory, or (last stage) U+ -> HBM.
 // ---- one Rosenbrock stage: forward substitution of dt*F(U_i) + sum cfac_j k_j, border
@@ -547,59 +439,7 @@ __device__ __forceinline__ void sys_stage(const Geom& g, const Buf& b, const Buf
       y[r] = v;
     }
   }
-  // ------------------------------------------------- border solution x_b
-  const int r0 = chunk * C;
-  const int bot0 = g.nhat - NB;
-  const bool flagged = (r0 + C > g.nhat - NB && r0 < g.nhat + NB);
-  if (flagged) {
-#pragma unroll
-    for (int r = 0; r < C; ++r) {
-      const int gr = r0 + r;
-      if (gr >= bot0 && gr < g.nhat + NB) sh.ytail[gr - bot0] = y[r];
-    }
-  }
-  __syncthreads();
-  double xb[NB];
-#pragma unroll
-  for (int c = 0; c < NB; ++c) xb[c] = 0.0;
-  if (flagged) {
-    double acc[NB];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) acc[c] = 0.0;
-    for (int r = 0; r < NB; ++r) {
-      const double yr = sh.ytail[r];
-#pragma unroll
-      for (int c = 0; c < NB; ++c) acc[c] = __fma_rn(sh.G[r * NB + c], yr, acc[c]);
-    }
-    double yb[NB];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) yb[c] = __dsub_rn(sh.ytail[NB + c], acc[c]);
-#pragma unroll
-    for (int r = 0; r < NB; ++r) {
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < NB; ++c) s = __fma_rn(sh.Sinv[r * NB + c], yb[c], s);
-      xb[r] = s;
-    }
-  }
   // --------------------------------------------------------------- backward
-  // border coupling of the few chunks that touch it: y <- y - W x_b on the fill rows,
-  // border rows <- x_b (applied once, ahead of both passes)
-  if (flagged) {
-#pragma unroll
-    for (int r = 0; r < C; ++r) {
-      const int gr = r0 + r;
-      double yv = y[r];
-      if (gr >= bot0 && gr < g.nhat) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c) yv = __fma_rn(-sh.W[(gr - bot0) * NB + c], xb[c], yv);
-      } else if (gr >= g.nhat && gr < g.nhat + NB) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c) if (gr - g.nhat == c) yv = xb[c];
-      }
-      y[r] = yv;
-    }
-  }
   auto load_y = [&](int r) -> double { return y[r]; };
   Aff mine;
   {
@@ -778,53 +618,6 @@ __device__ __forceinline__ void sys_stage_rt(const int I, const bool LAST, const
       y[r] = v;
     }
   }
-  // ------------------------------------------------- border solution x_b
-  const int r0 = chunk * C;
-  const int bot0 = g.nhat - NB;
-  const bool flagged = (r0 + C > g.nhat - NB && r0 < g.nhat + NB);
-  if (flagged) {
-#pragma unroll
-    for (int r = 0; r < C; ++r) {
-      const int gr = r0 + r;
-      if (gr >= bot0 && gr < g.nhat + NB) sh.ytail[gr - bot0] = y[r];
-    }
-  }
-  __syncthreads();
-  // border coupling of the few chunks that touch it: y <- y - W x_b on the fill rows,
-  // border rows <- x_b (applied once, ahead of both passes of the backward sweep)
-  if (flagged) {
-    double xb[NB], acc[NB];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) acc[c] = 0.0;
-    for (int r = 0; r < NB; ++r) {
-      const double yr = sh.ytail[r];
-#pragma unroll
-      for (int c = 0; c < NB; ++c) acc[c] = __fma_rn(sh.G[r * NB + c], yr, acc[c]);
-    }
-    double yb[NB];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) yb[c] = __dsub_rn(sh.ytail[NB + c], acc[c]);
-#pragma unroll
-    for (int r = 0; r < NB; ++r) {
-      double sacc = 0.0;
-#pragma unroll
-      for (int c = 0; c < NB; ++c) sacc = __fma_rn(sh.Sinv[r * NB + c], yb[c], sacc);
-      xb[r] = sacc;
-    }
-#pragma unroll
-    for (int r = 0; r < C; ++r) {
-      const int gr = r0 + r;
-      double yv = y[r];
-      if (gr >= bot0 && gr < g.nhat) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c) yv = __fma_rn(-sh.W[(gr - bot0) * NB + c], xb[c], yv);
-      } else if (gr >= g.nhat && gr < g.nhat + NB) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c) if (gr - g.nhat == c) yv = xb[c];
-      }
-      y[r] = yv;
-    }
-  }
   // --------------------------------------------------------------- backward
   Aff mine;
   {
@@ -968,7 +761,6 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
     sys_factor(g, lb, sys, a, sh.cst, sh, Lr, Ur, bad);
     SYS_CLK(1);
     if (bad) atomicOr(b.status + sys, 1);
-    sys_border(g, b, sys, a, sh, Lr, Ur);
     SYS_CLK(2);
     double emax = 0.0;
     if constexpr (LONG_TABLEAU) {
