@@ -212,11 +212,12 @@ def run_gpu(args):
     peak, peak_src = peaks()
     achieved = kernel_bytes(wk, dom) * units / (dom_ms / dom_n * 1e-3) / 1e9
     step_gbs = wk["Q"] * units * args.steps / (ms.value * 1e-3) / 1e9
-    traffic = None                              # DRAM bytes per launch of that kernel (ncu capture)
+    traffic, fp64_frac = None, None             # DRAM bytes per launch of that kernel (ncu capture)
     tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             per_node = json.load(f).get(args.workload, {}).get(dom)
+            fp64_frac = json.load(open(tpath)).get("_fp64_pipe_frac", {}).get(dom)
         if per_node:
             traffic = per_node * units          # DRAM bytes per launch (ncu, profiled kernel)
     roofline = {"bound": "hbm", "kernel": "tf_k_" + dom, "achieved": round(achieved, 1),
@@ -226,6 +227,8 @@ def run_gpu(args):
                 "step_achieved": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4),
                 "bytes_per_node_step": wk["Q"],
                 "family_ms_per_step": {k: round(v[0] / psteps, 4) for k, v in fam.items()}}
+    if fp64_frac is not None:
+        roofline["fp64_pipe_frac"] = fp64_frac  # ncu sm__inst_executed_pipe_fp64 (same capture)
     if dom == "sysstep":
         # the whole step is one launch that keeps the factor and the stage vectors on the SM:
         # DRAM traffic is ~16 B/node (traffic), far below the algorithmic Q the roofline is
