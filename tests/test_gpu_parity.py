@@ -447,6 +447,34 @@ def test_system_resident_step_equals_kernel_pipeline(sname, kw, mname, N):
             assert np.allclose(out[alt][k], out[1][k], rtol=1e-9, atol=0, equal_nan=True)
 
 
+@pytest.mark.parametrize("N", [5, 6, 7, 8, 9, 10, 11, 15, 16, 17, 18, 31, 33, 247, 248, 249, 255, 256,
+                               257, 258, 263, 264, 265, 266, 4087, 4088, 4089, 4095])
+def test_system_resident_ragged_sizes(N):
+    """Every position of the domain end relative to the chunk (8 nodes) and warp-block (256
+    nodes) boundaries, down to the smallest grid the banded solver takes (4P + 1 nodes): the
+    end-row pre-pass, the edge replication of the stencil windows and the padding rows."""
+    from triflow_b200 import schemes as S
+    from triflow_b200.ensemble import Ensemble
+    m = gmodel("burgers_up1")
+    rng = np.random.default_rng(N)
+    batch = 3
+    x = np.arange(N) * 0.2
+    pars = dict(k=np.array([0.05, 0.1, 0.3]), periodic=False)
+    U0 = np.cos(2 * np.pi * x / max(x[-1], 1.0)) + 0.3 * rng.standard_normal((batch, N))
+    for sname, kw in (("ROS3PRw", FX), ("Theta", dict(theta=1))):
+        out = []
+        for fused in (True, False):
+            ens = Ensemble(m, getattr(S, sname)(m, **kw), x, dict(U=U0), pars,
+                           hook=S.Dirichlet(U=(0.5, -0.5)), batch=batch)
+            ens.set_fusion(fused)
+            ens.step(0.05, 4)
+            out.append(ens.download())
+            assert not ens.state.status().any()
+        assert np.isfinite(out[0]).all()
+        for r in range(batch):
+            assert rel_traj_err(out[0][r], out[1][r]) <= 1e-12
+
+
 @pytest.mark.parametrize("batch,N", [(1500, 512), (450, 4096)])
 def test_system_resident_persistent_loop_many_systems_per_cta(batch, N):
     """More systems than resident CTAs: every CTA steps several systems in turn, the next
