@@ -182,9 +182,11 @@ __device__ __forceinline__ void sys_factor(const Geom& g, const Buf& lb, int sys
   if (nedge > SYS_EDGE_CHUNKS) asm volatile("trap;");         // cannot happen (bound above)
   // rows are dealt to the warps first (row k -> warp k mod nwarps): the row kinds (regular,
   // top, bottom, border, padding) take different branches, which would serialise inside a warp
-  const int nwarps_e = (int)blockDim.x >> 5;
-  for (int idx = (int)(threadIdx.x & 31) * nwarps_e + (int)(threadIdx.x >> 5); idx < nedge * SYS_RPC;
-       idx += blockDim.x) {
+  // (warp 0 is left out when there are others: its thread 0 is issuing the next system's TMA)
+  const int nwarps_a = (int)blockDim.x >> 5;
+  const int nwarps_e = nwarps_a > 1 ? nwarps_a - 1 : 1, w_e = (int)(threadIdx.x >> 5) - (nwarps_a > 1 ? 1 : 0);
+  for (int idx = (w_e >= 0 ? (int)(threadIdx.x & 31) * nwarps_e + w_e : nedge * SYS_RPC);
+       idx < nedge * SYS_RPC; idx += 32 * nwarps_e) {
     const int slot = idx / SYS_RPC, m = idx - slot * SYS_RPC;
     const int c = slot == 0 ? 0 : cfirst + slot - 1;
     sys_edge_row(c * M + m, g, lb.U + sys * vstride(g), lb, sys, a, cst, sh.edge + idx * WB);
@@ -731,30 +733,43 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
     const int cur = it & 1;
     int nxt = sys + gridDim.x;
     while (nxt < g.batch && !is_active(nxt)) nxt += gridDim.x;
-    if (nxt < g.batch && threadIdx.x == 0) {             // buffer cur^1 was released by the
-      mbar_expect_tx(&sh.bar[cur ^ 1], bytes);           // barrier that ended the last system
-      bulk_g2s(sUb[cur ^ 1], b.U + nxt * vs, bytes, &sh.bar[cur ^ 1]);
-    }
+    SYS_CLK(13);
     const double a = (b.asys != nullptr) ? b.asys[sys] : sd.a;
     const double dt = (b.dtsys != nullptr) ? b.dtsys[sys] : sd.dt;
     if (it == 0) {
       for (int k = threadIdx.x; k < NC2; k += T) sh.cst[k] = b.cst[(long long)sys * NC2 + k];
     }
-    // constants of the next system: loaded now, stored behind the barrier that ends this one
+    // The hand-over work between two systems is dealt to different warps so that it overlaps
+    // (thread 0 alone took ~2000 cycles for it): warp 0 issues the TMA of the next U, warp
+    // `w_err` writes the error estimate, warp `w_cst` fetches the next system's constants
+    // (loaded now, stored behind the barrier that ends this system).
+    const int nw_ = T >> 5, warp_ = (int)threadIdx.x >> 5, lane_ = (int)threadIdx.x & 31;
+    const int w_err = nw_ > 1 ? 1 : 0, w_cst = nw_ > 2 ? 2 : 0;
     double cst_next[CST_PT];
 #pragma unroll
     for (int k = 0; k < CST_PT; ++k) {
-      const int idx = threadIdx.x + k * T;
-      cst_next[k] = (nxt < g.batch && idx < NC2) ? b.cst[(long long)nxt * NC2 + idx] : 0.0;
+      const int idx = lane_ + k * 32;
+      cst_next[k] = 0.0;                              // predicated load: nothing waits for it here
+      if (warp_ == w_cst && nxt < g.batch && idx < NC2)
+        cst_next[k] = __ldg(b.cst + (long long)nxt * NC2 + idx);
     }
     const double* sU = sUb[cur];
     Buf lb = b;                                          // U and k_j of this system: shared memory
     lb.U = const_cast<double*>(sU) - sys * vs;
 #pragma unroll
     for (int q = 0; q < MAXS; ++q) lb.K[q] = (q < nk) ? sK + q * TC - sys * vs : nullptr;
+    SYS_CLK(14);
     mbar_wait(&sh.bar[cur], phase[cur]);
     phase[cur] ^= 1u;
+    SYS_CLK(15);
     __syncthreads();
+    // next system's U: issued here (~900 cycles for the issuing thread) because warp 0 has
+    // no row in the end-row pre-pass that follows; buffer cur^1 was released by the barrier
+    // that ended the last system
+    if (nxt < g.batch && threadIdx.x == 0) {
+      mbar_expect_tx(&sh.bar[cur ^ 1], bytes);
+      bulk_g2s(sUb[cur ^ 1], b.U + nxt * vs, bytes, &sh.bar[cur ^ 1]);
+    }
     double Lr[C][BETA], Ur[C][BETA + 1];
     int bad = 0;
     SYS_CLK(0);                                          // wait for U (TMA) + constants
@@ -798,11 +813,11 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
     __syncthreads();                                     // releases sU[cur], sK, sS, sh.*
 #pragma unroll
     for (int k = 0; k < CST_PT; ++k) {
-      const int idx = threadIdx.x + k * T;
-      if (nxt < g.batch && idx < NC2) sh.cst[idx] = cst_next[k];
+      const int idx = lane + k * 32;
+      if (warp == w_cst && nxt < g.batch && idx < NC2) sh.cst[idx] = cst_next[k];
     }
     SYS_CLK(4);
-    if (warp == 0) {                                     // max over the warps (NaN sticks)
+    if (warp == w_err) {                                 // max over the warps (NaN sticks)
       double e = 0.0;
       if (sd.has_pred) {
         e = (lane < (T >> 5)) ? sh.err[lane] : 0.0;
@@ -814,6 +829,7 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
       }
       if (lane == 0) b.err[sys] = e;
     }
+    SYS_CLK(12);
     sys = nxt;
     ++it;
   }
