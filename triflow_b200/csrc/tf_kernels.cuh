@@ -246,11 +246,10 @@ __device__ __forceinline__ void st_word(LbWord* p, double v, long long tag) {
       : "memory");
   (void)o0; (void)o1;
 }
-__device__ __forceinline__ bool ld_word(const LbWord* p, double& v, long long tag) {
-  long long a, t;
+__device__ __forceinline__ void ld_word(const LbWord* p, double& v, long long& t) {
+  long long a;
   asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(t) : "l"(p) : "memory");
   v = __longlong_as_double(a);
-  return t == tag;
 }
 template <class Mon>
 __device__ __forceinline__ void lb_publish(LbWord* dst, const Mon& m, long long tag, int lane) {
@@ -263,12 +262,24 @@ __device__ __forceinline__ void lb_publish(LbWord* dst, const Mon& m, long long 
     if (k0 + lane < Mon::K) st_word(dst + k0 + lane, v, tag);
   }
 }
+// Both records of a tile (inclusive prefix and aggregate) in ONE memory round trip: all 2K
+// loads are issued before the first tag is looked at (a compare right behind each load
+// serialises them: K round trips of ~1 us each per record, seen in the tile trace).
 template <class Mon>
-__device__ __forceinline__ bool lb_read(const LbWord* src, Mon& m, long long tag) {
-  bool ok = true;
+__device__ __forceinline__ void lb_read2(const LbWord* pi, const LbWord* pa, Mon& mi, Mon& ma,
+                                         long long FI, long long FA, bool& isI, bool& isA) {
+  long long ti[Mon::K], ta[Mon::K];
 #pragma unroll
-  for (int k = 0; k < Mon::K; ++k) ok = ld_word(src + k, m.d[k], tag) && ok;
-  return ok;
+  for (int k = 0; k < Mon::K; ++k) ld_word(pi + k, mi.d[k], ti[k]);
+#pragma unroll
+  for (int k = 0; k < Mon::K; ++k) ld_word(pa + k, ma.d[k], ta[k]);
+  isI = true;
+  isA = true;
+#pragma unroll
+  for (int k = 0; k < Mon::K; ++k) {
+    isI = isI && (ti[k] == FI);
+    isA = isA && (ta[k] == FA);
+  }
 }
 
 // Decoupled look-back over the tiles of one system.  Called by all 32 lanes of
@@ -311,8 +322,8 @@ __device__ Mon lookback(const Mon& aggregate, const Buf& b, long long gbase, int
         const LbWord* pa = (const LbWord*)b.lbagg + (gbase + t) * KMAX;
         do {                               // both records in one round trip
           Mon ea;
-          isI = lb_read(pi, e, FI);
-          const bool isA = lb_read(pa, ea, FA);
+          bool isA;
+          lb_read2(pi, pa, e, ea, FI, FA, isI, isA);
           if (!isI) e = ea;
           ready = isI || isA;
         } while (!ready && lane < need);
