@@ -314,28 +314,32 @@ __device__ Mon lookback(const Mon& aggregate, const Buf& b, long long gbase, int
     // two dependent memory round trips that queue behind the bulk loads of the sweep.
     int need = TF_LB_FIRST;               // lanes below `need` wait for their tile
     Mon w;
+    // Warp-uniform control flow: the whole warp repeats the round until the lanes below `need`
+    // have their record, every decision is a vote.  (A per-lane polling loop in front of the
+    // shuffles made the compiler emit them for a divergent warp: WARPSYNC.COLLECTIVE sequences
+    // in which warp 0 spent most of the look-back, ncu source view.)
+    Mon e = Mon::identity();
+    bool isI = true, ready = (t < 0), first = true;
     while (true) {
-      Mon e = Mon::identity();
-      bool isI = true, ready = true;
-      if (t >= 0) {
+      if (t >= 0 && (first || (lane < need && !ready))) {   // both records in one round trip
+        Mon ea;
+        bool isA;
         const LbWord* pi = (const LbWord*)b.lbinc + (gbase + t) * KMAX;
         const LbWord* pa = (const LbWord*)b.lbagg + (gbase + t) * KMAX;
-        do {                               // both records in one round trip
-          Mon ea;
-          bool isA;
-          lb_read2(pi, pa, e, ea, FI, FA, isI, isA);
-          if (!isI) e = ea;
-          ready = isI || isA;
-        } while (!ready && lane < need);
+        lb_read2(pi, pa, e, ea, FI, FA, isI, isA);
+        if (!isI) e = ea;
+        ready = isI || isA;
       }
+      first = false;
+      if (!__all_sync(0xffffffffu, ready || lane >= need)) continue;
       const unsigned mr = __ballot_sync(0xffffffffu, ready);
       const unsigned m2 = __ballot_sync(0xffffffffu, ready && isI);
       const int kr = (~mr == 0u) ? 32 : (__ffs(~mr) - 1);     // contiguous ready lanes
       const int kstop = __ffs(m2) - 1;                         // nearest inclusive (or start)
       const bool hit = (kstop >= 0 && kstop < kr);
       const int last = hit ? kstop : kr - 1;
-      e = select(t >= 0 && lane <= last, e, Mon::identity());
-      w = warp_reduce_rev(e, lane);
+      const Mon el = select(t >= 0 && lane <= last, e, Mon::identity());
+      w = warp_reduce_rev(el, lane);
       w = shfl_idx(w, 0);
 #ifdef TF_TRACE
       if (lane == 0 && tr_rounds < 4) {
@@ -347,7 +351,7 @@ __device__ Mon lookback(const Mon& aggregate, const Buf& b, long long gbase, int
       tr_rounds += 1;
       if (hit || absorbing(w) || kr == 32) tr_depth += last + 1;
 #endif
-      if (hit || absorbing(w)) { finished = true; break; }
+      if (__all_sync(0xffffffffu, hit || absorbing(w))) { finished = true; break; }
       if (kr == 32) break;                // full window of aggregates: go further back
       need = 32;                          // not conclusive: wait for the whole window
     }
