@@ -22,7 +22,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 TF_OK, TF_EINVAL, TF_ECUDA, TF_EMAXITER, TF_EDTMIN, TF_ESINGULAR = range(6)
 FAMILIES = ["factor", "border_fill", "fwd", "border_solve", "bwd", "update", "hook",
-            "pack", "eval", "sysstep"]
+            "pack", "eval", "sysstep", "gridstep"]
 
 
 class CudaUnavailable(RuntimeError):
@@ -67,7 +67,7 @@ def build_library(force=False):
     return LIB_PATH
 
 
-_KERNEL_SRCS = ["tf_kernels.cuh", "tf_sysstep.cuh", "tf_band.h", "tf_params.h", "tf_model_prelude.h"]
+_KERNEL_SRCS = ["tf_kernels.cuh", "tf_sysstep.cuh", "tf_gridstep.cuh", "tf_band.h", "tf_params.h", "tf_model_prelude.h"]
 
 
 def build_cubin(header, chunk_nodes, warps, fast_div=False):
@@ -86,7 +86,7 @@ def build_cubin(header, chunk_nodes, warps, fast_div=False):
         f.write(header)
         f.write('#include "tf_kernels.cuh"\n')
     tmp = cubin + ".tmp%d" % os.getpid()
-    cmd = [_nvcc(), *ARCH, "-O3", "-std=c++17", "-lineinfo", "-I", CSRC,
+    cmd = [_nvcc(), *ARCH, "-O3", "-std=c++17", "-lineinfo", "-diag-suppress", "550", "-I", CSRC,
            "-DTF_M=%d" % chunk_nodes, "-DTF_FAST_DIV=%d" % int(fast_div),
            *(["-DTF_MINB=%d" % minb] if minb else []), *extra, "-cubin", "-o", tmp, src]
     subprocess.check_call(cmd)

@@ -1,0 +1,1262 @@
+// Grid-resident implicit step: ONE cooperative launch does a whole Rosenbrock / Theta step of a
+// single long grid.  Every CTA owns one tile of the grid for the whole step.
+//
+// The per-kernel pipeline of tf_kernels.cuh runs factor -> border fill -> s x (fwd, bwd) as
+// 2 + 2s dependent launches; inside each launch all tiles load together, compute together and
+// look back together, and the factor, y and every stage vector make a round trip through
+// memory between launches (KS N = 2^20: 8 launches of 20-76 us for 46 us worth of HBM traffic).
+// Here the tiles are resident (cooperative launch, one tile per CTA, one CTA per SM):
+//
+//  * the L part of the factor never leaves shared memory, the forward-substitution result y
+//    never leaves the registers (the backward sweep of a stage runs in the same threads with
+//    the mirrored scan), stage-state halos are a neighbouring thread's shared-memory element;
+//  * tiles are coupled ONLY through 16-byte (value, tag) words (tf_kernels.cuh, LbWord):
+//    look-back records of the chunk scans, the P stage-state values at each tile edge, the
+//    L multipliers that cross a tile boundary, the periodic-border quantities (partial sums
+//    of G^T y and G^T W, x_b).  No fence, no grid-wide barrier, no kernel boundary: a tile
+//    starts the next phase as soon as its own neighbours are done;
+//  * the border fill of periodic systems (W = L^-1 E, G^T = F^T U^-1, tf_k_border_fill of the
+//    pipeline: a serial walk over the leading tiles) costs no phase of its own: both are
+//    forward recurrences, so their states ride on the scan of the first forward sweep (one fat
+//    affine map, one look-back), and every thread learns from its incoming state whether its
+//    rows of W and G are non-zero at all;
+//  * every thread owns G = 2 adjacent chunks (2M nodes) which sit in adjacent lanes of the
+//    lane-transposed layout, so the per-node cost of the scans halves and each thread's two
+//    recurrences interleave.
+//
+// Same algorithm as the pipeline (chunk scans with linear-fractional / affine maps, border
+// block for the periodic corners), agreeing with it to rounding; tests compare both paths.
+// Every wait is bounded: on time-out the status bit 4 is set and the launch still ends.
+//
+// Replaces, in one launch (reference file:line): compute_J_numpy + I - gamma*dt*J + factorized
+// (compilers.py:292-332, schemes.py:146-149), the s stages of ROW_general._fixed_step
+// (schemes.py:150-163), update and error norm (:164-174); Theta (:548-559) is the 1-stage case.
+//
+// Scope: scalar models (V == 1) without helper fields, s <= 3, one system (batch == 1),
+// tiles <= resident CTAs.  Everything else keeps the per-kernel pipeline.
+#pragma once
+
+#if (TF_NVAR == 1) && (TF_NHELP == 0)
+#define TF_HAS_GRIDSTEP 1
+
+#ifndef TF_GS_NT
+#define TF_GS_NT 448      /* max threads per CTA: 14 warps (4 per scheduler at most) x 128 registers */
+#endif
+#ifndef TF_GS_SPIN
+#define TF_GS_SPIN (1 << 19)
+#endif
+
+// Optional per-tile phase time stamps (cubin built with -DTF_GS_TRACE; tools/gs_trace.py):
+// globaltimer ns of thread 0 at the phase boundaries of the last step.
+#ifdef TF_GS_TRACE
+__device__ unsigned long long tf_gs_trace[256 * 32];
+#define GS_STAMP(ph) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tf_gs_trace[(cx.tile & 255) * 32 + (ph)] = t_; } } while (0)
+#else
+#define GS_STAMP(ph) do { } while (0)
+#endif
+
+namespace tfk {
+
+constexpr int GS_G = 2;                         // chunks per thread
+constexpr int GS_NT = TF_GS_NT;
+constexpr int GS_MAXW = GS_NT / 32;
+constexpr int GS_NPH = 1 + 2 * 3;               // look-back phases: factor, (fwd, bwd) x 3 stages
+constexpr int GS_STAGES = 3;
+static_assert(32 % GS_G == 0, "a thread's chunks lie in one warp-block");
+static_assert(C % BETA == 0, "streaming factorisation walks sub-blocks of BETA rows");
+
+// ---- fat affine map of the first forward sweep of a periodic system: the state of the
+//      substitution itself (PhiL, cy), of the NB columns of W = L^-1 E (same propagator PhiL)
+//      and of the NB columns of G^T = F^T U^-1 (forward substitution with U^T in "push" form:
+//      the state is the sum already pushed onto the next BETA rows; propagator PhiG).
+struct AffB {
+  static constexpr int K = 2 * BETA * BETA + BETA + 2 * NB * BETA;
+  double d[K];
+  __device__ __forceinline__ double* PhiL() { return d; }
+  __device__ __forceinline__ double* cy() { return d + BETA * BETA; }
+  __device__ __forceinline__ double* cW() { return d + BETA * BETA + BETA; }                 // [NB][BETA]
+  __device__ __forceinline__ double* PhiG() { return d + BETA * BETA + BETA + NB * BETA; }
+  __device__ __forceinline__ double* cG() { return d + 2 * BETA * BETA + BETA + NB * BETA; }  // [NB][BETA]
+  __device__ __forceinline__ const double* PhiL() const { return d; }
+  __device__ __forceinline__ const double* cy() const { return d + BETA * BETA; }
+  __device__ __forceinline__ const double* cW() const { return d + BETA * BETA + BETA; }
+  __device__ __forceinline__ const double* PhiG() const { return d + BETA * BETA + BETA + NB * BETA; }
+  __device__ __forceinline__ const double* cG() const { return d + 2 * BETA * BETA + BETA + NB * BETA; }
+  __device__ static __forceinline__ AffB identity() {
+    AffB m;
+#pragma unroll
+    for (int i = 0; i < K; ++i) m.d[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < BETA; ++i) { m.PhiL()[i * BETA + i] = 1.0; m.PhiG()[i * BETA + i] = 1.0; }
+    return m;
+  }
+  // `a` first (earlier rows), `b` second
+  __device__ static __forceinline__ AffB combine(const AffB& a, const AffB& b) {
+    AffB o;
+    tfb::mm<BETA>(b.PhiL(), a.PhiL(), o.PhiL());
+    tfb::mm<BETA>(b.PhiG(), a.PhiG(), o.PhiG());
+#pragma unroll
+    for (int i = 0; i < BETA; ++i) {
+      double sy = b.cy()[i];
+#pragma unroll
+      for (int k = 0; k < BETA; ++k) sy += b.PhiL()[i * BETA + k] * a.cy()[k];
+      o.cy()[i] = sy;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        double sw = b.cW()[c * BETA + i], sg = b.cG()[c * BETA + i];
+#pragma unroll
+        for (int k = 0; k < BETA; ++k) {
+          sw += b.PhiL()[i * BETA + k] * a.cW()[c * BETA + k];
+          sg += b.PhiG()[i * BETA + k] * a.cG()[c * BETA + k];
+        }
+        o.cW()[c * BETA + i] = sw;
+        o.cG()[c * BETA + i] = sg;
+      }
+    }
+    return o;
+  }
+};
+__device__ __forceinline__ bool absorbing(const AffB& m) {
+  bool z = true;
+#pragma unroll
+  for (int k = 0; k < BETA * BETA; ++k) z = z && (m.PhiL()[k] == 0.0) && (m.PhiG()[k] == 0.0);
+  return z;
+}
+constexpr int GS_KMAX = KMAX > AffB::K ? KMAX : AffB::K;
+
+// ---- record area (device memory, 16-byte words); offsets in words for `tiles` tiles
+struct GsRec {
+  LbWord* base;
+  int tiles;
+  __device__ __forceinline__ LbWord* lb(int ph, int tile, int which) const {   // which: 0 agg, 1 inc
+    return base + (((long long)ph * tiles + tile) * 2 + which) * GS_KMAX;
+  }
+  __device__ __forceinline__ long long o_halo() const { return (long long)GS_NPH * tiles * 2 * GS_KMAX; }
+  __device__ __forceinline__ LbWord* halo(int stage, int tile, int slot) const {
+    return base + o_halo() + (((long long)stage * tiles + tile) * 3 + slot) * P;
+  }
+  __device__ __forceinline__ long long o_lnext() const { return o_halo() + (long long)GS_STAGES * tiles * 3 * P; }
+  __device__ __forceinline__ LbWord* lnext(int tile) const { return base + o_lnext() + (long long)tile * BETA * BETA; }
+  __device__ __forceinline__ long long o_alive() const { return o_lnext() + (long long)tiles * BETA * BETA; }
+  __device__ __forceinline__ LbWord* alive(int tile) const { return base + o_alive() + tile; }
+  __device__ __forceinline__ long long o_gpart() const { return o_alive() + tiles; }
+  __device__ __forceinline__ LbWord* gpart(int stage, int tile) const {
+    return base + o_gpart() + ((long long)stage * tiles + tile) * NB;
+  }
+  __device__ __forceinline__ long long o_spart() const { return o_gpart() + (long long)GS_STAGES * tiles * NB; }
+  __device__ __forceinline__ LbWord* spart(int tile) const { return base + o_spart() + (long long)tile * NB * NB; }
+  __device__ __forceinline__ long long o_misc() const { return o_spart() + (long long)tiles * NB * NB; }
+  __device__ __forceinline__ LbWord* xb(int stage) const { return base + o_misc() + stage * NB; }
+  __device__ __forceinline__ LbWord* ftop() const { return base + o_misc() + GS_STAGES * NB; }
+  __device__ __forceinline__ long long o_err() const { return o_misc() + GS_STAGES * NB + NB * NB; }
+  __device__ __forceinline__ double* errt() const { return (double*)(base + o_err()); }   // [tiles] doubles
+};
+// (the host side mirrors the size of this area in tf_host.cu: gs_words)
+
+constexpr int GS_MAXTILES = 160;
+struct GsShared {
+  double scan[(GS_MAXW + 2) * GS_KMAX];   // warp totals, [GS_MAXW]: tile prefix
+  double cst[NC2];
+  double halo[2][P];                   // stage state left / right of the tile
+  double red[GS_MAXW][NB * NB > NB ? NB * NB : NB];
+  double gather[32 * NB * NB];         // words of other tiles collected by the last tile
+  double yb[2 * NB];                   // y of the last NB interior rows and of the border rows
+  double xb[NB];
+  double sinv[NB * NB];
+  double ftop[NB * NB];                // periodic corner block F_top (lives with the border rows)
+  double err[GS_MAXW];
+  int alist[GS_MAXTILES];              // last tile: the other tiles whose rows of W / G are non-zero
+  int nalive;
+  int epoch;
+  volatile int abort;
+};
+
+struct GsCtx {
+  GsRec rec;
+  GsShared* sh;
+  int* status;
+  long long tag;
+  int tile, tiles, T;
+};
+
+// ---- bounded waits on tagged words
+// (the first tile that gives up records where: status = 4 | site << 8 | tile << 16)
+__device__ __forceinline__ bool gs_aborted(GsCtx& cx, int spins, int site) {
+  if (cx.sh->abort) return true;
+  if ((spins & 1023) == 1023 && (ld_flag(cx.status) & 4)) { cx.sh->abort = 1; return true; }
+  if (spins > TF_GS_SPIN) {
+    const int code = 4 | (site << 8) | (cx.tile << 16);
+    int old = ld_flag(cx.status);
+    while (!(old & 4)) {
+      const int seen = atomicCAS(cx.status, old, old | code);
+      if (seen == old) break;
+      old = seen;
+    }
+    cx.sh->abort = 1;
+    return true;
+  }
+  return false;
+}
+__device__ __noinline__ double gs_wait(GsCtx& cx, const LbWord* p, int site) {
+  double v = 0.0;
+  long long t;
+  int spins = 0;
+  while (true) {
+    ld_word(p, v, t);
+    if (t == cx.tag) return v;
+    if (gs_aborted(cx, ++spins, site)) return 0.0;
+  }
+}
+__device__ __forceinline__ void gs_post(GsCtx& cx, LbWord* p, double v) { st_word(p, v, cx.tag); }
+
+// ---- decoupled look-back (see lookback() in tf_kernels.cuh; bounded, own record arrays)
+template <class Mon>
+__device__ __noinline__ Mon gs_lookback(const Mon& aggregate, GsCtx& cx, int ph, int lt, int lane) {
+  const long long FA = cx.tag * 4 + 1, FI = cx.tag * 4 + 2;
+  // logical tile lt of phase ph lives in slot lt (the backward phases number tiles from the end)
+  if (lt == 0) {
+    lb_publish(cx.rec.lb(ph, 0, 1), aggregate, FI, lane);
+    return Mon::identity();
+  }
+  lb_publish(cx.rec.lb(ph, lt, 0), aggregate, FA, lane);
+  Mon prefix = Mon::identity();
+  int look = lt - 1;
+  bool finished = false;
+  int spins = 0;
+  while (!finished) {
+    const int t = look - lane;
+    int need = TF_LB_FIRST;
+    Mon w;
+    Mon e = Mon::identity();
+    bool isI = true, ready = (t < 0), first = true;
+    while (true) {
+      if (t >= 0 && (first || (lane < need && !ready))) {
+        Mon ea;
+        bool isA;
+        lb_read2(cx.rec.lb(ph, t, 1), cx.rec.lb(ph, t, 0), e, ea, FI, FA, isI, isA);
+        if (!isI) e = ea;
+        ready = isI || isA;
+      }
+      first = false;
+      if (!__all_sync(0xffffffffu, ready || lane >= need)) {
+        const bool ab = gs_aborted(cx, ++spins, 16 + ph);
+        if (__any_sync(0xffffffffu, ab)) return Mon::identity();
+        continue;
+      }
+      const unsigned mr = __ballot_sync(0xffffffffu, ready);
+      const unsigned m2 = __ballot_sync(0xffffffffu, ready && isI);
+      const int kr = (~mr == 0u) ? 32 : (__ffs(~mr) - 1);
+      const int kstop = __ffs(m2) - 1;
+      const bool hit = (kstop >= 0 && kstop < kr);
+      const int last = hit ? kstop : kr - 1;
+      w = select(t >= 0 && lane <= last, e, Mon::identity());
+#pragma unroll 1
+      for (int d = 1; d < 32; d <<= 1) {                    // ordered reduction, lane 0 = nearest
+        const Mon o = shfl_down(w, d);
+        const Mon c = Mon::combine(o, w);
+        w = select(lane + d < 32, c, w);
+      }
+      w = shfl_idx(w, 0);
+      if (__all_sync(0xffffffffu, hit || absorbing(w))) { finished = true; break; }
+      if (kr == 32) break;
+      need = 32;
+    }
+    prefix = Mon::combine(w, prefix);
+    look -= 32;
+  }
+  lb_publish(cx.rec.lb(ph, lt, 1), Mon::combine(prefix, aggregate), FI, lane);
+  return prefix;
+}
+
+// ---- exclusive prefix of every thread's element over (thread, tile) order, or the mirrored
+//      order (REV: backward substitution).  Warp shuffles -> shared memory -> look-back.
+template <class Mon, bool REV>
+__device__ __noinline__ Mon gs_scan(const Mon& mine, GsCtx& cx, int ph) {
+  double* smem = cx.sh->scan;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = cx.T >> 5;
+  const int ml = REV ? 31 - lane : lane;
+  const int mw = REV ? nwarps - 1 - warp : warp;
+  Mon incl = mine;
+  // (level loops are rolled: the kernel is one long straight line, code size matters)
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    const Mon o = REV ? shfl_down(incl, d) : shfl_up(incl, d);
+    const Mon c = Mon::combine(o, incl);
+    incl = select(ml >= d, c, incl);
+  }
+  Mon excl = REV ? shfl_down(incl, 1) : shfl_up(incl, 1);
+  excl = select(ml == 0, Mon::identity(), excl);
+  if (ml == 31) {
+#pragma unroll
+    for (int k = 0; k < Mon::K; ++k) smem[mw * Mon::K + k] = incl.d[k];
+  }
+  __syncthreads();
+  Mon w = Mon::identity();
+  if (lane < nwarps) {
+#pragma unroll
+    for (int k = 0; k < Mon::K; ++k) w.d[k] = smem[lane * Mon::K + k];
+  }
+  Mon wi = w;
+#pragma unroll 1
+  for (int d = 1; d < GS_MAXW; d <<= 1) {
+    const Mon o = shfl_up(wi, d);
+    const Mon c = Mon::combine(o, wi);
+    wi = select(lane >= d, c, wi);
+  }
+  Mon we = shfl_idx(wi, mw > 0 ? mw - 1 : 0);
+  we = select(mw == 0, Mon::identity(), we);
+  const Mon local = Mon::combine(we, excl);
+  if (cx.tiles == 1) return local;
+  if (warp == 0) {
+    const Mon total = shfl_idx(wi, nwarps - 1);
+    const int lt = REV ? cx.tiles - 1 - cx.tile : cx.tile;
+    const Mon tp = gs_lookback(total, cx, ph, lt, lane);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < Mon::K; ++k) smem[GS_MAXW * GS_KMAX + k] = tp.d[k];
+    }
+  }
+  __syncthreads();
+  Mon tp;
+#pragma unroll
+  for (int k = 0; k < Mon::K; ++k) tp.d[k] = smem[GS_MAXW * GS_KMAX + k];
+  return Mon::combine(tp, local);
+}
+
+// ---- geometry of a thread's chunks
+struct GsThread {
+  int t, T;            // thread in tile, threads per tile
+  int chunk0;          // first chunk (global index)
+  int blk, cl;         // warp-block and lane of the first chunk in the lane-transposed layout
+  bool active;
+  __device__ __forceinline__ long long cb(int h) const { return ((long long)blk * C) * 32 + cl + h; }
+};
+// shared-memory layouts (thread-minor: conflict-free)
+__device__ __forceinline__ int gs_sl(int r, int q, int h, int t, int T) { return ((r * BETA + q) * GS_G + h) * T + t; }
+__device__ __forceinline__ int gs_ss(int r, int h, int t, int T) { return (r * GS_G + h) * T + t; }
+
+// stage state of node j (any tile) from global memory: U + ((alpha_0 k_0 + ...)).  Valid for
+// nodes of the own tile (same-CTA writes, ordered by a barrier) and, at stage 0, for any node.
+template <int I>
+__device__ __forceinline__ double gs_state_global(const Buf& b, int j, const TfStepDesc& sd) {
+  const long long a = vidx(j, 0);
+  double u = b.U[a];
+  if (I > 0) {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < I; ++q) {
+      const double term = __dmul_rn(sd.alpha[I][q], b.K[q][a]);
+      acc = (q == 0) ? term : __dadd_rn(acc, term);
+    }
+    u = __dadd_rn(u, acc);
+  }
+  return u;
+}
+// stage state of node jm (already wrapped / clamped into [0, N)) wherever it lives
+template <int I>
+__device__ __noinline__ double gs_node_value(GsCtx& cx, const Geom& g, const Buf& b, int jm,
+                                             const TfStepDesc& sd) {
+  const int TN = cx.T * GS_G * M;
+  const int ot = jm / TN;
+  if (I == 0 || ot == cx.tile) return gs_state_global<I>(b, jm, sd);
+  const int loc = jm - ot * TN;
+  if (loc < P) return gs_wait(cx, cx.rec.halo(I, ot, 0) + loc, 10);
+  if (loc >= TN - P) return gs_wait(cx, cx.rec.halo(I, ot, 1) + (loc - (TN - P)), 11);
+  return gs_wait(cx, cx.rec.halo(I, ot, 2) + (jm - (g.N - P)), 12);
+}
+
+// ------------------------------------------------------------------ factorisation
+// pass 1 of one chunk: its linear-fractional map (factor_body_stream of tf_kernels.cuh)
+__device__ __noinline__ void gs_factor_pass1(const Geom& g, const Buf& b, int chunk, double a,
+                                             const double* cst, Star& out, int& bad) {
+  constexpr int NODES = M + EX;
+  constexpr int NSB = C / BETA;
+  const int i0 = chunk * M;
+  const bool allreg = i0 >= P && i0 + NODES <= g.N - 2 * P;
+  double win[NF][NODES + 2 * P];
+  load_windows<NODES, 0>(win, i0, g, b, 0, nullptr);
+  Star mine = Star::identity();
+  double cur[BETA][WB], nxt[BETA][WB];
+#pragma unroll
+  for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, b, 0, a, cst, allreg);
+#pragma unroll
+  for (int k = 0; k < NSB; ++k) {
+#pragma unroll
+    for (int r = 0; r < BETA; ++r) node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, b, 0, a, cst, allreg);
+    double Dh[BETA * BETA], Z[BETA * 2 * BETA], Rr[BETA * BETA];
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int c = 0; c < BETA; ++c) {
+        Dh[r * BETA + c] = cur[r][BETA + c - r] - mine.P()[r * BETA + c];
+        Z[r * 2 * BETA + c] = (c <= r) ? cur[r][BETA + BETA + c - r] : 0.0;
+        Z[r * 2 * BETA + BETA + c] = mine.Q()[r * BETA + c];
+        Rr[r * BETA + c] = (c >= r) ? nxt[r][BETA + c - BETA - r] : 0.0;
+      }
+    tfb::solve_inplace<BETA, 2 * BETA>(Dh, Z);
+    double Z1[BETA * BETA], Z2[BETA * BETA];
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int c = 0; c < BETA; ++c) {
+        Z1[r * BETA + c] = Z[r * 2 * BETA + c];
+        Z2[r * BETA + c] = Z[r * 2 * BETA + BETA + c];
+      }
+    Star nx;
+    tfb::mm<BETA>(Rr, Z1, nx.P());
+    tfb::mm<BETA>(Rr, Z2, nx.Q());
+#pragma unroll
+    for (int q = 0; q < BETA * BETA; ++q) nx.R()[q] = mine.R()[q];
+    tfb::mma<BETA>(mine.S(), Z2, nx.R());
+    tfb::mm<BETA>(mine.S(), Z1, nx.S());
+    mine = nx;
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int d = 0; d < WB; ++d) cur[r][d] = nxt[r][d];
+  }
+#pragma unroll
+  for (int q = 0; q < Star::K; ++q)
+    if (!(fabs(mine.d[q]) < 1e300)) bad = 1;
+  out = mine;
+}
+
+// pass 2 of one chunk: elimination with the true incoming update X (in/out); U rows -> global,
+// L multipliers -> shared memory (own rows) / Lout (what is left on the next chunk's first rows)
+__device__ __noinline__ void gs_factor_pass2(const Geom& g, const Buf& b, const GsThread& th, int h,
+                                             double a, const double* cst, double* sL, double* X,
+                                             double (&Lout)[BETA][BETA], double* phiG, int& bad) {
+  constexpr int NODES = M + EX;
+  constexpr int NSB = C / BETA;
+  const int chunk = th.chunk0 + h;
+  const int i0 = chunk * M;
+  const bool allreg = i0 >= P && i0 + NODES <= g.N - 2 * P;
+  double win[NF][NODES + 2 * P];
+  load_windows<NODES, 0>(win, i0, g, b, 0, nullptr);
+  double* Ug = b.Uf + th.cb(h) * (BETA + 1) - (long long)(th.cl + h) * BETA;   // row r, entry q: [(r*(BETA+1)+q)*32]
+  double Lprev[BETA][BETA];
+#pragma unroll
+  for (int r = 0; r < BETA; ++r)
+#pragma unroll
+    for (int q = 0; q < BETA; ++q) Lprev[r][q] = 0.0;
+  // homogeneous solutions of the push recurrence of G^T = F^T U^-1 (see AffB): hG[j][t] is
+  // what solution j has pushed onto the row t + 1 ahead
+  double hG[BETA][BETA];
+#pragma unroll
+  for (int j = 0; j < BETA; ++j)
+#pragma unroll
+    for (int t = 0; t < BETA; ++t) hG[j][t] = (j == t) ? 1.0 : 0.0;
+  double cur[BETA][WB], nxt[BETA][WB];
+#pragma unroll
+  for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, b, 0, a, cst, allreg);
+#pragma unroll
+  for (int k = 0; k < NSB; ++k) {
+#pragma unroll
+    for (int r = 0; r < BETA; ++r) node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, b, 0, a, cst, allreg);
+    double A2[2 * BETA][WB];
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int d = 0; d < WB; ++d) {
+        A2[r][d] = cur[r][d];
+        A2[BETA + r][d] = (BETA + r + d - BETA < BETA) ? nxt[r][d] : 0.0;
+      }
+    double Uf[BETA][BETA + 1], Lown[BETA][BETA], Lnext[BETA][BETA], Xo[BETA * BETA];
+    tfb::ChunkLU<BETA, BETA>::run2x(A2, X, Uf, Lown, Lnext, Xo, bad);
+#pragma unroll
+    for (int r = 0; r < BETA; ++r) {
+      const int row = k * BETA + r;
+#pragma unroll
+      for (int q = 0; q <= BETA; ++q) Ug[(long long)(row * (BETA + 1) + q) * 32] = Uf[r][q];
+#pragma unroll
+      for (int j = 0; j < BETA; ++j) {
+        const double gv = -(hG[j][0] * Uf[r][0]);
+#pragma unroll
+        for (int t = 0; t < BETA; ++t) hG[j][t] = ((t + 1 < BETA) ? hG[j][t + 1 < BETA ? t + 1 : 0] : 0.0) + Uf[r][t + 1] * gv;
+      }
+#pragma unroll
+      for (int q = 1; q <= BETA; ++q) {
+        if (q <= r) sL[gs_sl(row, q - 1, h, th.t, th.T)] = Lown[r][q - 1];
+        else if (k > 0) sL[gs_sl(row, q - 1, h, th.t, th.T)] = Lprev[r][q - 1];
+        // k == 0, q > r: multipliers with respect to the previous chunk's pivots (filled by it)
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int q = 0; q < BETA; ++q) Lprev[r][q] = Lnext[r][q];
+#pragma unroll
+    for (int q = 0; q < BETA * BETA; ++q) X[q] = Xo[q];
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int d = 0; d < WB; ++d) cur[r][d] = nxt[r][d];
+  }
+#pragma unroll
+  for (int r = 0; r < BETA; ++r)
+#pragma unroll
+    for (int q = 0; q < BETA; ++q) Lout[r][q] = Lprev[r][q];
+#pragma unroll
+  for (int i = 0; i < BETA; ++i)
+#pragma unroll
+    for (int j = 0; j < BETA; ++j) phiG[i * BETA + j] = hG[j][i];
+}
+
+__device__ __forceinline__ void gs_factor(const Geom& g, const Buf& b, GsCtx& cx, const GsThread& th,
+                                          double a, double* sL, double (&phiG)[GS_G][BETA * BETA]) {
+  GsShared& sh = *cx.sh;
+  int bad = 0;
+  Star mine = Star::identity();
+  if (th.active) {
+    Star m0, m1;
+    gs_factor_pass1(g, b, th.chunk0, a, sh.cst, m0, bad);
+    gs_factor_pass1(g, b, th.chunk0 + 1, a, sh.cst, m1, bad);
+    mine = Star::combine(m0, m1);
+  }
+  GS_STAMP(1);
+  const Star pre = gs_scan<Star, false>(mine, cx, 0);
+  GS_STAMP(2);
+#pragma unroll
+  for (int h = 0; h < GS_G; ++h)
+#pragma unroll
+    for (int q = 0; q < BETA * BETA; ++q) phiG[h][q] = (q / BETA == q % BETA) ? 1.0 : 0.0;
+  if (th.active) {
+    double X[BETA * BETA];
+#pragma unroll
+    for (int q = 0; q < BETA * BETA; ++q) X[q] = pre.P()[q];
+    double Lout[BETA][BETA];
+#pragma unroll 1
+    for (int h = 0; h < GS_G; ++h) {
+      gs_factor_pass2(g, b, th, h, a, sh.cst, sL, X, Lout, phiG[h], bad);
+      // multipliers left on the next chunk's first BETA rows (entries q > r)
+      const bool cross = (h == GS_G - 1) && (th.t == th.T - 1);
+      if (!cross) {
+        const int h2 = (h + 1 < GS_G) ? h + 1 : 0;
+        const int t2 = (h + 1 < GS_G) ? th.t : th.t + 1;
+#pragma unroll
+        for (int r = 0; r < BETA; ++r)
+#pragma unroll
+          for (int q = r + 1; q <= BETA; ++q) sL[gs_sl(r, q - 1, h2, t2, th.T)] = Lout[r][q - 1];
+      } else if (cx.tile + 1 < cx.tiles) {
+#pragma unroll
+        for (int r = 0; r < BETA; ++r)
+#pragma unroll
+          for (int q = r + 1; q <= BETA; ++q) gs_post(cx, cx.rec.lnext(cx.tile) + r * BETA + q - 1, Lout[r][q - 1]);
+      }
+    }
+    if (bad) atomicOr(cx.status, 1);
+  }
+  // first rows of the tile: multipliers with respect to the previous tile's pivots
+  if (th.t == 0) {
+#pragma unroll
+    for (int r = 0; r < BETA; ++r)
+#pragma unroll
+      for (int q = r + 1; q <= BETA; ++q)
+        sL[gs_sl(r, q - 1, 0, 0, th.T)] =
+            (cx.tile == 0) ? 0.0 : gs_wait(cx, cx.rec.lnext(cx.tile - 1) + r * BETA + q - 1, 1);
+  }
+  __syncthreads();
+  // the periodic corner block F_top was assembled with the border rows (last tile); the first
+  // chunk of the system needs it for its rows of G
+  if (g.periodic && threadIdx.x < NB * NB) {
+    const double v = b.btab[2 * NB * NB + threadIdx.x];
+    if (cx.tiles == 1) sh.ftop[threadIdx.x] = v;
+    else if (cx.tile == cx.tiles - 1) gs_post(cx, cx.rec.ftop() + threadIdx.x, v);
+  }
+  GS_STAMP(3);
+}
+
+// ------------------------------------------------------------------ border block
+// L multiplier (row gr, entry q) of the own tile from shared memory
+__device__ __forceinline__ double gs_sl_at(const double* sL, int gr, int q, int row0, int T) {
+  const int loc = gr - row0;
+  const int ch = loc / C, r = loc - ch * C;
+  return sL[gs_sl(r, q, ch % GS_G, ch / GS_G, T)];
+}
+
+// right-hand sides of the fill recurrences: -a * E_top (rows of W) / -a * F_top (rows of G);
+// non-zero only in the first NB rows of the system
+__device__ __forceinline__ double gs_fw(const double* bt, double a, int gr, int c) {
+  return (gr < NB) ? -(a * bt[gr * NB + c]) : 0.0;
+}
+__device__ __forceinline__ double gs_fg(const double* ftop, double a, int gr, int c) {
+  return (gr < NB) ? -(a * ftop[c * NB + gr]) : 0.0;
+}
+
+// partial sum over this tile's rows of G[r][i] * W[r][j] -> sh.red[0][i*NB+j]; a thread
+// counts the rows it knows to be non-zero (its own if it is alive, and the bottom rows)
+__device__ __forceinline__ void gs_gw_partial(const Geom& g, const Buf& b, GsCtx& cx, const GsThread& th,
+                                              bool th_alive, bool with_bottom) {
+  GsShared& sh = *cx.sh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = cx.T >> 5;
+  const int bot0 = g.nhat - NB;
+  double part[NB][NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) part[i][j] = 0.0;
+  if (th.active) {
+#pragma unroll 1
+    for (int h = 0; h < GS_G; ++h) {
+      const int r0 = (th.chunk0 + h) * C;
+      if (th_alive || (with_bottom && r0 + C > bot0 && r0 < g.nhat)) {
+#pragma unroll
+        for (int r = 0; r < C; ++r) {
+          const int gr = r0 + r;
+          if (gr < g.nhat && (th_alive || (with_bottom && gr >= bot0))) {
+            double gv[NB], wv[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) { gv[c] = b.Gb[fidx(gr, c, NB)]; wv[c] = b.Wb[fidx(gr, c, NB)]; }
+#pragma unroll
+            for (int i = 0; i < NB; ++i)
+#pragma unroll
+              for (int j = 0; j < NB; ++j) part[i][j] = __fma_rn(gv[i], wv[j], part[i][j]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      double v = part[i][j];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) sh.red[warp][i * NB + j] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < NB * NB) {
+    double v = 0.0;
+    for (int w = 0; w < nwarps; ++w) v += sh.red[w][threadIdx.x];
+    sh.red[0][threadIdx.x] = v;          // (column x is read and written by thread x only)
+  }
+  __syncthreads();
+}
+
+// Sum over the alive tiles (sh.alist) of `per` words each, in list order, added to
+// sh.red[0][0 .. per).  All threads of the (last) tile take part; one memory round trip per
+// 32 tiles.
+template <int KIND>   // 0: spart words, 1: gpart words of stage `which`
+__device__ __noinline__ void gs_gather_sum(GsCtx& cx, int which, int per, int site) {
+  GsShared& sh = *cx.sh;
+  for (int base = 0; base < sh.nalive; base += 32) {
+    const int n = sh.nalive - base < 32 ? sh.nalive - base : 32;
+    for (int idx = threadIdx.x; idx < n * per; idx += cx.T)
+      sh.gather[idx] = gs_wait(cx, (KIND == 0 ? cx.rec.spart(sh.alist[base + idx / per])
+                                              : cx.rec.gpart(which, sh.alist[base + idx / per])) + idx % per, site);
+    __syncthreads();
+    if ((int)threadIdx.x < per) {
+      double v = sh.red[0][threadIdx.x];
+      for (int t = 0; t < n; ++t) v += sh.gather[t * per + threadIdx.x];
+      sh.red[0][threadIdx.x] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// Last tile, once per step: which other tiles have non-zero rows of W / G; the bottom rows of
+// W and G (natural coupling of the last NB interior rows to the border, superposed on what
+// the fill left there); S = (I - a Ab) - G^T W and its inverse.
+__device__ __noinline__ void gs_border_last(const Geom& g, const Buf& b, GsCtx& cx, const GsThread& th,
+                                            double a, const double* sL, bool th_alive) {
+  GsShared& sh = *cx.sh;
+  const int TR = cx.T * GS_G * C;
+  const int row0 = cx.tile * TR;
+  const int bot0 = g.nhat - NB;
+  const double* bt = b.btab;
+  // alive flags of the other tiles (parallel polls), compacted in tile order
+  for (int t = threadIdx.x; t < cx.tiles - 1; t += cx.T)
+    sh.alist[t] = (g.periodic && gs_wait(cx, cx.rec.alive(t), 6) != 0.0) ? 1 : 0;
+  if (threadIdx.x < 2 * NB) {
+    const bool isW = threadIdx.x < NB;
+    const int c = isW ? threadIdx.x : threadIdx.x - NB;
+    double loc[NB];
+    for (int j = 0; j < NB; ++j) {
+      const int gr = bot0 + j;
+      double v = -(a * (isW ? bt[1 * NB * NB + j * NB + c] : bt[3 * NB * NB + c * NB + j]));
+      for (int q = 1; q <= BETA; ++q) {
+        const int jj = j - q;
+        if (jj < 0) break;
+        const double coef = isW ? gs_sl_at(sL, gr, q - 1, row0, cx.T)
+                                : b.Uf[fidx(gr - q, q, BETA + 1)] * b.Uf[fidx(gr - q, 0, BETA + 1)];
+        v -= coef * loc[jj];
+      }
+      loc[j] = v;
+      const double out = isW ? v : v * b.Uf[fidx(gr, 0, BETA + 1)];
+      double* dst = (isW ? b.Wb : b.Gb) + fidx(gr, c, NB);
+      *dst = *dst + out;               // (rows the fill did not reach were zeroed by their owner)
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int na = 0;
+    for (int t = 0; t < cx.tiles - 1; ++t)
+      if (sh.alist[t]) sh.alist[na++] = t;
+    sh.nalive = na;
+  }
+  gs_gw_partial(g, b, cx, th, th_alive, true);               // own rows -> sh.red[0]
+  gs_gather_sum<0>(cx, 0, NB * NB, 7);
+  if (threadIdx.x == 0) {
+    double S[NB * NB], I[NB * NB];
+    for (int i = 0; i < NB; ++i)
+      for (int j = 0; j < NB; ++j) {
+        S[i * NB + j] = __dsub_rn(__fma_rn(-a, bt[4 * NB * NB + i * NB + j], (i == j) ? 1.0 : 0.0),
+                                  sh.red[0][i * NB + j]);
+        I[i * NB + j] = (i == j) ? 1.0 : 0.0;
+      }
+    tfb::solve_inplace<NB, NB>(S, I);
+    bool bad = false;
+    for (int k = 0; k < NB * NB; ++k) {
+      sh.sinv[k] = I[k];
+      b.Sinv[k] = I[k];
+      if (!(fabs(I[k]) < 1e300)) bad = true;
+    }
+    if (bad) atomicOr(cx.status, 2);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ one stage
+// th_alive / tile_alive: this thread's / this tile's rows of W and G may be non-zero (set by
+// stage 0, used by every stage)
+template <int I, bool LAST>
+__device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx, const GsThread& th,
+                                         const TfStepDesc& sd, double a, const double* sL, double* sS,
+                                         const double (&phiG)[GS_G][BETA * BETA], bool& th_alive,
+                                         bool& tile_alive, double& emax) {
+  GsShared& sh = *cx.sh;
+  const int T = cx.T;
+  const int TN = T * GS_G * M;
+  const bool last_tile = cx.tile == cx.tiles - 1;
+  const double* cst = sh.cst;
+  const int bot0 = g.nhat - NB;
+  double y[GS_G][C];
+  // ---------------------------------------------------------------- forward
+  {
+    double own[GS_G][C];
+#pragma unroll
+    for (int h = 0; h < GS_G; ++h)
+#pragma unroll
+      for (int r = 0; r < C; ++r) own[h][r] = 0.0;
+    if (th.active) {
+#pragma unroll
+      for (int h = 0; h < GS_G; ++h)
+#pragma unroll
+        for (int r = 0; r < C; ++r) {
+          const long long aidx = th.cb(h) + (long long)r * 32;
+          double u = b.U[aidx];
+          if (I > 0) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < I; ++q) {
+              const double term = __dmul_rn(sd.alpha[I][q], b.K[q][aidx]);
+              acc = (q == 0) ? term : __dadd_rn(acc, term);
+            }
+            u = __dadd_rn(u, acc);
+          }
+          own[h][r] = u;
+        }
+    }
+    // ghost cells inside the padding: the slots of nodes N .. N+P-1 carry the state of the
+    // wrapped / clamped neighbour (compilers.py:257-264), so the windows below need no
+    // special case at the end of the domain.  (The slots may lie in a warp-block beyond the
+    // system's last one: they only exist in shared memory.)
+    bool ghost = false;
+    if (last_tile) {
+#pragma unroll
+      for (int h = 0; h < GS_G; ++h) {
+        const int i0 = (th.chunk0 + h) * M;
+        if (i0 + M > g.N && i0 < g.N + P) {
+          ghost = true;
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            const int j = i0 + m;
+            if (j >= g.N && j < g.N + P) own[h][m] = gs_node_value<I>(cx, g, b, map_node(j, g), sd);
+          }
+        }
+      }
+    }
+    if (th.active || ghost) {
+#pragma unroll
+      for (int h = 0; h < GS_G; ++h)
+#pragma unroll
+        for (int r = 0; r < C; ++r) sS[gs_ss(r, h, th.t, T)] = own[h][r];
+    }
+    // stage state at the P nodes left and right of the tile
+    if (threadIdx.x < 2 * P) {
+      const int side = threadIdx.x / P, k = threadIdx.x - side * P;
+      const int j = side == 0 ? cx.tile * TN - P + k : (cx.tile + 1) * TN + k;
+      // (right of a tile that ends in padding: no real node reads it, nobody publishes it)
+      sh.halo[side][k] = (j < g.N + P) ? gs_node_value<I>(cx, g, b, map_node(j, g), sd) : 0.0;
+    }
+    // the first chunk of a periodic system starts the recurrences of W and G: F_top
+    if (I == 0 && g.periodic && cx.tiles > 1 && cx.tile == 0 && threadIdx.x >= 2 * P &&
+        threadIdx.x < 2 * P + NB * NB)
+      sh.ftop[threadIdx.x - 2 * P] = gs_wait(cx, cx.rec.ftop() + (threadIdx.x - 2 * P), 5);
+    __syncthreads();
+    double rhs_all[GS_G][C];
+    Aff mh[GS_G];
+    mh[0] = Aff::identity();
+    mh[1] = Aff::identity();
+    if (th.active) {
+#pragma unroll
+      for (int h = 0; h < GS_G; ++h) {
+        const int i0 = (th.chunk0 + h) * M;
+        double win[NF][M + 2 * P];
+#pragma unroll
+        for (int w = 0; w < M + 2 * P; ++w) {
+          const int rel = w - P;
+          double v;
+          if (rel < 0) {
+            if (h > 0) v = own[h > 0 ? h - 1 : 0][M + rel];
+            else v = (th.t > 0) ? sS[gs_ss(M + rel, GS_G - 1, th.t - 1, T)] : sh.halo[0][P + rel];
+          } else if (rel >= M) {
+            if (h < GS_G - 1) v = own[h < GS_G - 1 ? h + 1 : 0][rel - M];
+            else v = (th.t < T - 1) ? sS[gs_ss(rel - M, 0, th.t + 1, T)] : sh.halo[1][rel - M];
+          } else {
+            v = own[h][rel];
+          }
+          win[0][w] = v;
+        }
+        RecState rs;
+        rs.init();
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          const int i = i0 + m;
+          double fe[V];
+          fe[0] = 0.0;
+          {
+            TfNodeIn in;
+            node_inputs<M>(in, win, m, i, g, b, 0);
+            tf_model_F<FD>(cst, in, fe);
+          }
+          double rhs = __dmul_rn(sd.dt, fe[0]);
+#pragma unroll
+          for (int q = 0; q < I; ++q) rhs = __fma_rn(sd.cfac[I][q], b.K[q][th.cb(h) + (long long)m * 32], rhs);
+          rhs = (i < g.N) ? rhs : 0.0;
+          rhs_all[h][m] = rhs;
+          double coef[BETA];
+#pragma unroll
+          for (int q = 0; q < BETA; ++q) coef[q] = sL[gs_sl(m, q, h, th.t, T)];
+          rs.step(coef, rhs, 1.0);
+        }
+        rs.to_map(mh[h]);
+      }
+    }
+    GS_STAMP(4 + 6 * I);
+    double sv[BETA];
+    double ws[NB][BETA], pg[NB][BETA];       // incoming states of the fill recurrences (stage 0)
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+#pragma unroll
+      for (int t = 0; t < BETA; ++t) { ws[c][t] = 0.0; pg[c][t] = 0.0; }
+    const bool first_chunk = (cx.tile == 0 && th.t == 0);
+    if (I == 0 && g.periodic) {
+      // fat map: the substitution + the NB columns of W + the NB columns of G
+      AffB mb[GS_G];
+#pragma unroll
+      for (int h = 0; h < GS_G; ++h) {
+        mb[h] = AffB::identity();
+#pragma unroll
+        for (int k = 0; k < BETA * BETA; ++k) { mb[h].PhiL()[k] = mh[h].Phi()[k]; mb[h].PhiG()[k] = phiG[h][k]; }
+#pragma unroll
+        for (int k = 0; k < BETA; ++k) mb[h].cy()[k] = mh[h].c()[k];
+      }
+      if (first_chunk && th.active) {
+        // particular solutions of the system's first chunk (zero incoming state)
+        const double* Ug = b.Uf + th.cb(0) * (BETA + 1) - (long long)(th.cl) * BETA;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+          double s[BETA], p[BETA];
+#pragma unroll
+          for (int t = 0; t < BETA; ++t) { s[t] = 0.0; p[t] = 0.0; }
+#pragma unroll
+          for (int r = 0; r < C; ++r) {
+            double v = gs_fw(b.btab, a, r, c);
+#pragma unroll
+            for (int q = 0; q < BETA; ++q) v -= sL[gs_sl(r, q, 0, 0, T)] * s[q];
+#pragma unroll
+            for (int q = BETA - 1; q > 0; --q) s[q] = s[q - 1];
+            s[0] = v;
+            const double gv = (gs_fg(sh.ftop, a, r, c) - p[0]) * Ug[(long long)(r * (BETA + 1)) * 32];
+#pragma unroll
+            for (int t = 0; t < BETA; ++t)
+              p[t] = ((t + 1 < BETA) ? p[t + 1 < BETA ? t + 1 : 0] : 0.0) + Ug[(long long)(r * (BETA + 1) + t + 1) * 32] * gv;
+          }
+#pragma unroll
+          for (int t = 0; t < BETA; ++t) { mb[0].cW()[c * BETA + t] = s[t]; mb[0].cG()[c * BETA + t] = p[t]; }
+        }
+      }
+      const AffB mineB = AffB::combine(mb[0], mb[1]);
+      const AffB pre = gs_scan<AffB, false>(mineB, cx, 1);
+#pragma unroll
+      for (int t = 0; t < BETA; ++t) sv[t] = pre.cy()[t];
+#pragma unroll
+      for (int c = 0; c < NB; ++c)
+#pragma unroll
+        for (int t = 0; t < BETA; ++t) { ws[c][t] = pre.cW()[c * BETA + t]; pg[c][t] = pre.cG()[c * BETA + t]; }
+    } else {
+      const Aff mine = Aff::combine(mh[0], mh[1]);
+      const Aff pre = gs_scan<Aff, false>(mine, cx, 1 + 2 * I);
+#pragma unroll
+      for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
+    }
+    GS_STAMP(5 + 6 * I);
+    if (th.active) {
+#pragma unroll
+      for (int h = 0; h < GS_G; ++h)
+#pragma unroll
+        for (int r = 0; r < C; ++r) {
+          double v = rhs_all[h][r];
+#pragma unroll
+          for (int q = 0; q < BETA; ++q) v -= sL[gs_sl(r, q, h, th.t, T)] * sv[q];
+#pragma unroll
+          for (int q = BETA - 1; q > 0; --q) sv[q] = sv[q - 1];
+          sv[0] = v;
+          y[h][r] = v;
+        }
+    }
+    // ------------------------------------------------------------ border fill (once per step)
+    if (I == 0) {
+      th_alive = false;
+      if (g.periodic && th.active) {
+        th_alive = first_chunk;
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+#pragma unroll
+          for (int t = 0; t < BETA; ++t) th_alive = th_alive || (ws[c][t] != 0.0) || (pg[c][t] != 0.0);
+        if (th_alive) {
+          // this thread's rows of W = L^-1 E and G^T = F^T U^-1 with the true incoming states
+#pragma unroll 1
+          for (int h = 0; h < GS_G; ++h) {
+            const int r0 = (th.chunk0 + h) * C;
+            const double* Ug = b.Uf + th.cb(h) * (BETA + 1) - (long long)(th.cl + h) * BETA;
+#pragma unroll
+            for (int r = 0; r < C; ++r) {
+              const int gr = r0 + r;
+              const double inv = Ug[(long long)(r * (BETA + 1)) * 32];
+              double uq[BETA];
+#pragma unroll
+              for (int t = 0; t < BETA; ++t) uq[t] = Ug[(long long)(r * (BETA + 1) + t + 1) * 32];
+              const long long o = (th.cb(h) + (long long)r * 32) * NB - (long long)(th.cl + h) * (NB - 1);
+#pragma unroll
+              for (int c = 0; c < NB; ++c) {
+                double v = gs_fw(b.btab, a, gr, c);
+#pragma unroll
+                for (int q = 0; q < BETA; ++q) v -= sL[gs_sl(r, q, h, th.t, T)] * ws[c][q];
+#pragma unroll
+                for (int q = BETA - 1; q > 0; --q) ws[c][q] = ws[c][q - 1];
+                ws[c][0] = v;
+                b.Wb[o + (long long)c * 32] = v;
+                const double gv = (gs_fg(sh.ftop, a, gr, c) - pg[c][0]) * inv;
+#pragma unroll
+                for (int t = 0; t < BETA; ++t)
+                  pg[c][t] = ((t + 1 < BETA) ? pg[c][t + 1 < BETA ? t + 1 : 0] : 0.0) + uq[t] * gv;
+                b.Gb[o + (long long)c * 32] = gv;
+              }
+            }
+          }
+        }
+      }
+      // bottom rows the fill did not reach start from zero (gs_border_last adds onto them)
+      if (last_tile && th.active && !th_alive) {
+#pragma unroll
+        for (int h = 0; h < GS_G; ++h) {
+          const int r0 = (th.chunk0 + h) * C;
+          if (r0 + C > bot0 && r0 < g.nhat) {
+#pragma unroll
+            for (int r = 0; r < C; ++r)
+              if (r0 + r >= bot0 && r0 + r < g.nhat) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c) { b.Wb[fidx(r0 + r, c, NB)] = 0.0; b.Gb[fidx(r0 + r, c, NB)] = 0.0; }
+              }
+          }
+        }
+      }
+      tile_alive = __syncthreads_or(th_alive ? 1 : 0) != 0;
+      if (last_tile) {
+        gs_border_last(g, b, cx, th, a, sL, th_alive);
+      } else {
+        if (threadIdx.x == 0) gs_post(cx, cx.rec.alive(cx.tile), tile_alive ? 1.0 : 0.0);
+        if (tile_alive) {
+          gs_gw_partial(g, b, cx, th, th_alive, false);
+          if (threadIdx.x < NB * NB) gs_post(cx, cx.rec.spart(cx.tile) + threadIdx.x, sh.red[0][threadIdx.x]);
+        }
+      }
+    }
+  }
+  // ---------------------------------------------------------------- border solve
+  {
+    // partial sums of G^T y over the rows of the fill (border_solution_* of the pipeline)
+    if (tile_alive) {
+      double acc[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) acc[c] = 0.0;
+      if (th_alive) {
+#pragma unroll
+        for (int h = 0; h < GS_G; ++h) {
+          const int r0 = (th.chunk0 + h) * C;
+#pragma unroll
+          for (int r = 0; r < C; ++r)
+            if (r0 + r < bot0) {
+#pragma unroll
+              for (int c = 0; c < NB; ++c) acc[c] += b.Gb[fidx(r0 + r, c, NB)] * y[h][r];
+            }
+        }
+      }
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], d);
+        if (lane == 0) sh.red[warp][c] = acc[c];
+      }
+      __syncthreads();
+      if (threadIdx.x < NB) {
+        double v = 0.0;
+        for (int w = 0; w < (T >> 5); ++w) v += sh.red[w][threadIdx.x];
+        if (last_tile) sh.red[0][threadIdx.x] = v;
+        else gs_post(cx, cx.rec.gpart(I, cx.tile) + threadIdx.x, v);
+      }
+      __syncthreads();
+    } else if (last_tile) {
+      if (threadIdx.x < NB) sh.red[0][threadIdx.x] = 0.0;
+      __syncthreads();
+    }
+    // x_b = S^-1 (y_b - G^T y): the last tile owns the bottom rows and the border rows
+    if (last_tile) {
+      if (th.active) {
+#pragma unroll
+        for (int h = 0; h < GS_G; ++h) {
+          const int r0 = (th.chunk0 + h) * C;
+          if (r0 + C > bot0 && r0 < g.nhat + NB) {
+#pragma unroll
+            for (int r = 0; r < C; ++r) {
+              const int k = r0 + r - bot0;
+              if (k >= 0 && k < 2 * NB) sh.yb[k] = y[h][r];
+            }
+          }
+        }
+      }
+      gs_gather_sum<1>(cx, I, NB, 8);             // (starts with a barrier-free poll,
+      __syncthreads();                                        //  ends with one)
+      if (threadIdx.x == 0) {
+        double acc[NB];
+        for (int c = 0; c < NB; ++c) acc[c] = sh.red[0][c];
+        for (int j = 0; j < NB; ++j) {                        // natural coupling of the last rows
+          const int gr = bot0 + j;
+          for (int c = 0; c < NB; ++c) acc[c] = __fma_rn(b.Gb[fidx(gr, c, NB)], sh.yb[j], acc[c]);
+        }
+        double ybv[NB];
+        for (int c = 0; c < NB; ++c) ybv[c] = __dsub_rn(sh.yb[NB + c], acc[c]);
+        for (int r = 0; r < NB; ++r) {
+          double s = 0.0;
+          for (int c = 0; c < NB; ++c) s = __fma_rn(sh.sinv[r * NB + c], ybv[c], s);
+          sh.xb[r] = s;
+          if (sh.nalive > 0) gs_post(cx, cx.rec.xb(I) + r, s);
+        }
+      }
+      __syncthreads();
+    } else if (tile_alive) {
+      if (threadIdx.x < NB) sh.xb[threadIdx.x] = gs_wait(cx, cx.rec.xb(I) + threadIdx.x, 9);
+      __syncthreads();
+    }
+  }
+  GS_STAMP(6 + 6 * I);
+  // --------------------------------------------------------------- backward
+  // y <- y - W x_b on the rows of the fill, border rows <- x_b
+  if (th.active && (th_alive || last_tile)) {
+    double xb[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) xb[c] = sh.xb[c];
+#pragma unroll
+    for (int h = 0; h < GS_G; ++h) {
+      const int r0 = (th.chunk0 + h) * C;
+      if (th_alive || (r0 + C > bot0 && r0 < g.nhat + NB)) {
+#pragma unroll
+        for (int r = 0; r < C; ++r) {
+          const int gr = r0 + r;
+          if (gr < g.nhat && (th_alive || gr >= bot0)) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) y[h][r] = __fma_rn(-b.Wb[fidx(gr, c, NB)], xb[c], y[h][r]);
+          } else if (gr >= g.nhat && gr < g.nhat + NB) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) if (gr - g.nhat == c) y[h][r] = xb[c];
+          }
+        }
+      }
+    }
+  }
+  Aff mine = Aff::identity();
+  if (th.active) {
+    Aff mh[GS_G];
+#pragma unroll
+    for (int h = GS_G - 1; h >= 0; --h) {
+      const double* Ug = b.Uf + th.cb(h) * (BETA + 1) - (long long)(th.cl + h) * BETA;
+      RecState rs;
+      rs.init();
+#pragma unroll
+      for (int r = C - 1; r >= 0; --r) {
+        double coef[BETA];
+#pragma unroll
+        for (int q = 0; q < BETA; ++q) coef[q] = Ug[(long long)(r * (BETA + 1) + q + 1) * 32];
+        rs.step(coef, y[h][r], Ug[(long long)(r * (BETA + 1)) * 32]);
+      }
+      rs.to_map(mh[h]);
+    }
+    mine = Aff::combine(mh[GS_G - 1], mh[0]);           // mirrored order: the later chunk first
+  }
+  GS_STAMP(7 + 6 * I);
+  const Aff pre = gs_scan<Aff, true>(mine, cx, 2 + 2 * I);
+  GS_STAMP(8 + 6 * I);
+  if (th.active) {
+    double sv[BETA];
+#pragma unroll
+    for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
+#pragma unroll
+    for (int h = GS_G - 1; h >= 0; --h) {
+      const double* Ug = b.Uf + th.cb(h) * (BETA + 1) - (long long)(th.cl + h) * BETA;
+      const int i0 = (th.chunk0 + h) * M;
+#pragma unroll
+      for (int r = C - 1; r >= 0; --r) {
+        double v = y[h][r];
+#pragma unroll
+        for (int q = 0; q < BETA; ++q) v -= Ug[(long long)(r * (BETA + 1) + q + 1) * 32] * sv[q];
+        v *= Ug[(long long)(r * (BETA + 1)) * 32];
+#pragma unroll
+        for (int q = BETA - 1; q > 0; --q) sv[q] = sv[q - 1];
+        sv[0] = v;
+        const long long aidx = th.cb(h) + (long long)r * 32;
+        double k = v;
+        double kprev[I > 0 ? I : 1];
+#pragma unroll
+        for (int q = 0; q < I; ++q) {
+          kprev[q] = b.K[q][aidx];
+          k = __fma_rn(-sd.cfac[I][q], kprev[q], k);
+        }
+        if (!LAST) {
+          b.K[I][aidx] = k;
+          // stage state of the next stage at the tile edges (and the last P real nodes)
+          const int i = i0 + r;
+          const int loc = i - cx.tile * TN;
+          const bool e0 = loc < P, e1 = loc >= TN - P, e2 = last_tile && i >= g.N - P && i < g.N;
+          if (cx.tiles > 1 && (e0 || e1 || e2)) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q <= I; ++q) {
+              const double term = __dmul_rn(sd.alpha[I + 1][q], q < I ? kprev[q < I ? q : 0] : k);
+              acc = (q == 0) ? term : __dadd_rn(acc, term);
+            }
+            const double nv = __dadd_rn(b.U[aidx], acc);
+            if (e0) gs_post(cx, cx.rec.halo(I + 1, cx.tile, 0) + loc, nv);
+            if (e1) gs_post(cx, cx.rec.halo(I + 1, cx.tile, 1) + (loc - (TN - P)), nv);
+            if (e2) gs_post(cx, cx.rec.halo(I + 1, cx.tile, 2) + (i - (g.N - P)), nv);
+          }
+        } else {
+          double acc = 0.0, accp = 0.0;
+#pragma unroll
+          for (int q = 0; q <= I; ++q) {
+            const double kq = (q < I) ? kprev[q < I ? q : 0] : k;
+            const double t = __dmul_rn(sd.b[q], kq);
+            acc = (q == 0) ? t : __dadd_rn(acc, t);
+            const double tp = __dmul_rn(sd.bp[q], kq);
+            accp = (q == 0) ? tp : __dadd_rn(accp, tp);
+          }
+          const double un = __dadd_rn(b.U[aidx], acc);
+          b.Un[aidx] = un;
+          if (sd.has_pred) {
+            const double e = fabs(__dsub_rn(un, __dadd_rn(un, accp)));
+            emax = (e > emax || e != e) ? e : emax;
+          }
+        }
+      }
+    }
+  }
+  if (!LAST) __syncthreads();       // k_I of the tile is in place before the next stage reads it
+  GS_STAMP(9 + 6 * I);
+}
+
+}  // namespace tfk
+
+extern "C" __global__ void __launch_bounds__(tfk::GS_NT, 1) tf_k_gridstep(tfk::Geom g, tfk::Buf b,
+                                                                          TfStepDesc sd) {
+  using namespace tfk;
+  extern __shared__ __align__(128) double dsm_gs[];
+  __shared__ GsShared sh;
+  const int T = blockDim.x;
+  double* sL = dsm_gs;                                   // [C][BETA][G][T]
+  double* sS = dsm_gs + (size_t)T * GS_G * C * BETA;     // [C][G][T]
+  GsCtx cx;
+  cx.rec.base = (LbWord*)b.gs;
+  cx.rec.tiles = (int)gridDim.x;
+  cx.sh = &sh;
+  cx.status = b.status;
+  cx.tile = (int)blockIdx.x;
+  cx.tiles = (int)gridDim.x;
+  cx.T = T;
+  if (threadIdx.x == 0) {
+    sh.epoch = ld_flag(b.ctl + 0);
+    sh.abort = 0;
+    sh.nalive = 0;
+  }
+  for (int k = threadIdx.x; k < NC2; k += T) sh.cst[k] = b.cst[k];
+  __syncthreads();
+  cx.tag = sh.epoch;
+  GsThread th;
+  th.t = (int)threadIdx.x;
+  th.T = T;
+  th.chunk0 = (cx.tile * T + th.t) * GS_G;
+  th.blk = th.chunk0 >> 5;
+  th.cl = th.chunk0 & 31;
+  th.active = th.blk < g.nblk;
+  const double a = sd.a;
+  GS_STAMP(0);
+  double phiG[GS_G][BETA * BETA];
+  gs_factor(g, b, cx, th, a, sL, phiG);
+  double emax = 0.0;
+  bool th_alive = false, tile_alive = false;
+  switch (sd.s) {
+    case 1:
+      gs_stage<0, true>(g, b, cx, th, sd, a, sL, sS, phiG, th_alive, tile_alive, emax);
+      break;
+    case 2:
+      gs_stage<0, false>(g, b, cx, th, sd, a, sL, sS, phiG, th_alive, tile_alive, emax);
+      gs_stage<1, true>(g, b, cx, th, sd, a, sL, sS, phiG, th_alive, tile_alive, emax);
+      break;
+    default:
+      gs_stage<0, false>(g, b, cx, th, sd, a, sL, sS, phiG, th_alive, tile_alive, emax);
+      gs_stage<1, false>(g, b, cx, th, sd, a, sL, sS, phiG, th_alive, tile_alive, emax);
+      gs_stage<2, true>(g, b, cx, th, sd, a, sL, sS, phiG, th_alive, tile_alive, emax);
+      break;
+  }
+  // error estimate: per-tile maximum, reduced by the last CTA to finish
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double o = __shfl_xor_sync(0xffffffffu, emax, d);
+    emax = (o > emax || o != o) ? o : emax;
+  }
+  if (lane == 0) sh.err[warp] = emax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (T >> 5); ++w) emax = (sh.err[w] > emax || sh.err[w] != sh.err[w]) ? sh.err[w] : emax;
+    double* errt = cx.rec.errt();
+    errt[cx.tile] = emax;
+    __threadfence();
+    const unsigned d = atomicAdd((unsigned*)(b.ctl + 2), 1u);
+    if (d == gridDim.x - 1) {
+      __threadfence();
+      double e = 0.0;
+      for (int t = 0; t < cx.tiles; ++t) {
+        const double v = __ldcg(errt + t);
+        e = (v > e || v != v) ? v : e;
+      }
+      b.err[0] = e;
+      b.ctl[2] = 0;
+      b.ctl[0] = (sh.epoch >= (1 << 28)) ? 1 : sh.epoch + 1;
+    }
+  }
+}
+
+#endif  // V == 1 && no helper fields

@@ -562,11 +562,14 @@ __device__ __forceinline__ void node_inputs(TfNodeIn& in, const double (&win)[NF
 // P nodes) or the padding.  Dynamic indexing on purpose: rare path.
 __device__ __noinline__ void assemble_special(int i, const Geom& g, const double* jv, double a,
                                               double* rows /* [V][WB] */, double* btab) {
+  // btab == nullptr: the node is evaluated a second time as one of the extra rows of the
+  // previous chunk; only its owner writes the border tables (two writers would race on the
+  // zero-then-accumulate below when they run in different warps)
   for (int k = 0; k < V * WB; ++k) rows[k] = 0.0;
   const int nint = g.N - P;                 // interior nodes
   if (i >= nint) {                          // border or padding: identity row in the band
     for (int e = 0; e < V; ++e) rows[e * WB + BETA] = 1.0;
-    if (i >= g.N) return;
+    if (i >= g.N || btab == nullptr) return;
     double* Ft = btab + 2 * NB * NB;
     double* Fb = btab + 3 * NB * NB;
     double* Ab = btab + 4 * NB * NB;
@@ -584,18 +587,20 @@ __device__ __noinline__ void assemble_special(int i, const Geom& g, const double
     }
     return;
   }
-  double* Et = btab;
-  double* Eb = btab + NB * NB;
+  double dummy[NB * NB];
+  double* Et = btab ? btab : dummy;
+  double* Eb = btab ? btab + NB * NB : dummy;
   const bool top = i < P, bot = i >= g.N - 2 * P;
-  if (top) for (int e = 0; e < V; ++e) for (int c = 0; c < NB; ++c) Et[(i * V + e) * NB + c] = 0.0;
-  if (bot) for (int e = 0; e < V; ++e) for (int c = 0; c < NB; ++c)
+  const bool wr = btab != nullptr;
+  if (top && wr) for (int e = 0; e < V; ++e) for (int c = 0; c < NB; ++c) Et[(i * V + e) * NB + c] = 0.0;
+  if (bot && wr) for (int e = 0; e < V; ++e) for (int c = 0; c < NB; ++c)
     Eb[((i - (g.N - 2 * P)) * V + e) * NB + c] = 0.0;
   for (int kk = 0; kk < NNZ; ++kk) {
     const int e = tf_j_eq(kk), var = tf_j_var(kk), off = tf_j_off(kk);
     const int j = map_node(i + off, g);
     if (j < nint) {
       rows[e * WB + BETA + (j - i) * V + var - e] += jv[kk];
-    } else {
+    } else if (wr) {
       const int c = (j - nint) * V + var;
       if (top) Et[(i * V + e) * NB + c] += jv[kk];
       else Eb[((i - (g.N - 2 * P)) * V + e) * NB + c] += jv[kk];
@@ -641,7 +646,7 @@ __device__ __forceinline__ void assemble_rows(double (&A)[C + BETA][WB], int i0,
         }
       } else {
         double tmp[V * WB];
-        assemble_special(i, g, jv, a, tmp, b.btab + (long long)sys * 5 * NB * NB);
+        assemble_special(i, g, jv, a, tmp, m < M ? b.btab + (long long)sys * 5 * NB * NB : nullptr);
 #pragma unroll
         for (int e = 0; e < V; ++e)
 #pragma unroll
@@ -850,7 +855,7 @@ __device__ __forceinline__ void node_row(double (&row)[WB], const double (&win)[
     double jvl[NNZ], tmp[WB];                     // the rare path works on private copies
 #pragma unroll
     for (int kk = 0; kk < NNZ; ++kk) jvl[kk] = jv[kk];
-    assemble_special(i, g, jvl, a, tmp, b.btab + (long long)sys * 5 * NB * NB);
+    assemble_special(i, g, jvl, a, tmp, m < M ? b.btab + (long long)sys * 5 * NB * NB : nullptr);
 #pragma unroll
     for (int d = 0; d < WB; ++d) row[d] = tmp[d];
   }
@@ -1749,6 +1754,7 @@ TF_BWD_KERNEL(tf_k_bwd2l, 2, 1)
 TF_BWD_KERNEL(tf_k_bwdg, -1, -1)
 
 #include "tf_sysstep.cuh"
+#include "tf_gridstep.cuh"
 
 // Dirichlet-style hook: U[var][0] = left, U[var][N-1] = right  (README.md:126-129)
 extern "C" __global__ void tf_k_dirichlet(Geom g, double* __restrict__ U, const double* __restrict__ dir,
@@ -1795,12 +1801,16 @@ extern "C" __global__ void tf_k_ctl_init(int batch, TfCtl* c, double* dtsys, dou
 extern "C" __global__ void tf_k_ctl_update(int batch, TfCtl* c, double* dtsys, double* asys, int* act,
                                            int* commit, const double* err, int* n_active,
                                            double tol, double safety, int max_iter, double dt_min,
-                                           double gamma) {
+                                           double gamma, int* status) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= batch) return;
   commit[s] = 0;
   if (!act[s]) return;
   TfCtl k = c[s];
+  // a bad pivot only counts when the attempt it belongs to is taken (a rejected attempt with
+  // too large a step is retried with a smaller one, like the reference's loop)
+  const int bad = status[s];
+  status[s] = 0;
   const double e = err[s];
   k.nfs += 1;
   if (k.phase == 1) {                       // the exact step to the target is always taken
@@ -1825,6 +1835,7 @@ extern "C" __global__ void tf_k_ctl_update(int batch, TfCtl* c, double* dtsys, d
       else if (dt_min > 0.0 && k.dt_int < dt_min) { k.fail = 4; k.phase = 2; act[s] = 0; }
     }
   }
+  if (commit[s] && bad && !k.fail) { k.fail = 5; k.phase = 2; act[s] = 0; }   // TF_ESINGULAR
   dtsys[s] = k.dt_try;
   asys[s] = gamma * k.dt_try;
   c[s] = k;
@@ -1834,11 +1845,11 @@ extern "C" __global__ void tf_k_ctl_update(int batch, TfCtl* c, double* dtsys, d
 // U <- U_new for the members whose attempt was accepted
 extern "C" __global__ void tf_k_commit(Geom g, double* __restrict__ U, const double* __restrict__ Un,
                                        const int* __restrict__ commit) {
-  const int sys = blockIdx.y;
+  const int sys = blockIdx.x;                 // (batch in grid.x: no 65535 limit)
   if (!commit[sys]) return;
   const long long vs = vstride(g);
-  for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < vs;
-       a += (long long)gridDim.x * blockDim.x)
+  for (long long a = blockIdx.y * (long long)blockDim.x + threadIdx.x; a < vs;
+       a += (long long)gridDim.y * blockDim.x)
     U[sys * vs + a] = Un[sys * vs + a];
 }
 

@@ -42,6 +42,7 @@ struct TfBuf {
   double* lbagg;        /* [batch*tiles][KMAX] tile aggregates, 16-byte (value, tag) words */
   double* lbinc;        /* [batch*tiles][KMAX] inclusive prefixes, same format */
   double* gpart;        /* [batch*fwd_tiles][NB] per-tile partial G^T y of the last fwd */
+  void* gs;             /* record area of the grid-resident step (tf_gridstep.cuh), 16-byte words */
 };
 
 struct TfStage {
