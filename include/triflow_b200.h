@@ -143,15 +143,23 @@ int tf_ensemble_advance(tf_state_t st, tf_scheme_t sc, double t, double dt, doub
  * core/schemes.py:146-149).  Off by default; uploading new constants invalidates it. */
 int tf_state_set_factor_reuse(tf_state_t st, int enable);
 
-/* System-resident stepping (on by default): when a whole system fits one CTA (tridiagonal
- * scalar model, non-periodic, N <= 4096 and (stages + 2) vectors of the system within 200 KB
- * of shared memory) one launch does the whole step of
- * ROW_general._fixed_step (core/schemes.py:142-174) with U and the stage vectors in shared
- * memory and the factor in registers; 0 selects the per-kernel pipeline (same algorithm,
- * results agree to rounding). */
-int tf_state_set_fusion(tf_state_t st, int enable);   /* 2: on, run-time stage kernel for every tableau */
+/* Which kernels run ROW_general._fixed_step / Theta.__call__ (core/schemes.py:142-174,548-559);
+ * every choice runs the same algorithm and agrees with the others to rounding.
+ *   1 (default) automatic:
+ *       - system-resident kernel when a whole system fits one CTA (tridiagonal scalar model,
+ *         non-periodic, N <= 4096, (stages + 2) vectors within 200 KB of shared memory): one
+ *         launch per step, U and the stage vectors in shared memory, the factor in registers;
+ *       - grid-resident kernel for one long grid where it pays (scalar model without helper
+ *         fields, stages <= 3, pentadiagonal or wider, N >= 786432): one cooperative launch
+ *         per step, one resident tile per CTA, tiles coupled through tagged 16-byte words;
+ *       - else the per-kernel pipeline (factor, border fill, 2 sweeps per stage).
+ *   0 the per-kernel pipeline only
+ *   2 the run-time-stage variant of the system-resident kernel for every tableau
+ *   3 the grid-resident kernel wherever it applies (any N) */
+int tf_state_set_fusion(tf_state_t st, int enable);
 
-/* status bits per system (bit0 bad pivot, bit1 singular border block) */
+/* status bits per system: bit0 bad pivot, bit1 singular border block, bit2 a tile of the
+ * grid-resident step gave up waiting for a neighbour (bits 8.. say where) */
 int tf_state_status(tf_state_t st, int* status);
 /* number of kernels launched on this state's context since creation */
 long long tf_ctx_launch_count(tf_ctx_t ctx);

@@ -353,7 +353,35 @@ def dump_traj():
         print("traj", k, np.asarray(v).shape)
 
 
+def _ens_member_full(job):
+    idx, k, c_, N, steps, dt = job
+    c = W.ensemble(N, [0])
+    m = ref_model("advdiff")
+    pars = dict(k=float(k), c=float(c_), periodic=False)
+    _, U, _ = run_fixed(m, _scheme(m, "ROS3PRw", time_stepping=False), c["x"], c["fields"],
+                        pars, dt, steps, hook=W.readme_hook)
+    return idx, U
+
+
+def dump_ensemble_full():
+    """cfg 5 at its real size: the 64 parity members of SURVEY.md §8d (incl. 0, 127, 128,
+    16384, 32767) at N = 4096 x 100 steps, each an independent run of the reference."""
+    import multiprocessing as mp
+    mem = W.ensemble_parity_subset(59)
+    c = W.ensemble(4096, mem)
+    jobs = [(i, c["pars"]["k"][i], c["pars"]["c"][i], 4096, 100, c["dt"]) for i in range(len(mem))]
+    with mp.get_context("fork").Pool(min(8, os.cpu_count() or 1)) as pool:
+        res = dict(pool.map(_ens_member_full, jobs))
+    finals = np.array([res[i] for i in range(len(mem))])
+    np.savez_compressed(os.path.join(HERE, "traj_ens4096.npz"), members=mem, final=finals)
+    print("traj_ens4096", finals.shape)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ens4096":
+        dump_ensemble_full()
+        sys.exit(0)
     dump_expressions()
     dump_fj()
     dump_traj()
+    dump_ensemble_full()

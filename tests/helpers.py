@@ -49,6 +49,11 @@ def traj():
     return np.load(os.path.join(GOLDEN, "traj.npz"))
 
 
+def traj_ens4096():
+    """cfg 5 at its real grid size: 64 members x 100 steps run by the reference itself."""
+    return np.load(os.path.join(GOLDEN, "traj_ens4096.npz"))
+
+
 def csc_triplet(J):
     J = J.tocsc().copy()
     J.sum_duplicates()

@@ -251,6 +251,31 @@ def test_ensemble_members_golden():
         assert rel_traj_err(U[idx], g["ensemble_512_final"][idx]) <= TRAJ_TOL
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_ensemble_members_full_grid_golden(fused):
+    """cfg 5 at its real grid size N = 4096, directly against the reference: the 64 parity
+    members of SURVEY.md §8d (0, 127, 128, 16384, 32767 + 59 seeded ones), 100 steps, on the
+    system-resident kernel (the headline path) and on the per-kernel pipeline."""
+    from helpers import traj_ens4096
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.ensemble import Ensemble
+    g = traj_ens4096()
+    mem = g["members"]
+    assert len(mem) == 64 and {0, 127, 128, 16384, 32767} <= set(mem.tolist())
+    c = W.ensemble(4096, mem)
+    m = gmodel("advdiff")
+    ens = Ensemble(m, S.ROS3PRw(m, **FX), c["x"], c["fields"], c["pars"],
+                   hook=S.Dirichlet(U=(1.0, 0.0)), batch=len(mem))
+    ens.set_fusion(fused)
+    n0 = ens_launches(ens)
+    ens.step(c["dt"], 100)
+    U = ens.download()
+    if fused:
+        assert ens_launches(ens) - n0 <= 1 + 2 * 100     # one step kernel + one hook per step
+    worst = max(rel_traj_err(U[i], g["final"][i]) for i in range(len(mem)))
+    assert worst <= TRAJ_TOL
+
+
 def test_ensemble_full_size_properties():
     """N=4096 members at full grid size: every member equals the same member run
     alone (independence), and members with equal parameters agree bit-for-bit."""
@@ -693,3 +718,157 @@ def test_host_pipeline_equals_blocking_ensemble():
     with pytest.raises(RuntimeError):
         pipe.step_host(h_in, h_out, cb["dt"], 1)
     pipe.close()
+
+
+# ------------------------------------------------ grid-resident single-launch step
+def _grid_case(name, N):
+    """(model name, scheme factory, x, fields, pars, dt, hook) of a single-system case."""
+    from triflow_b200 import schemes as S, workloads as W
+    rng = np.random.default_rng(N)
+    if name == "ks":
+        c = W.kuramoto(N)
+        return "ks", lambda m: S.ROS3PRw(m, **FX), c["x"], c["fields"], c["pars"], c["dt"], S.null_hook
+    if name == "ks_edge":
+        c = W.kuramoto(N)
+        return ("ks", lambda m: S.ROS2(m), c["x"], c["fields"], dict(periodic=False), c["dt"],
+                S.null_hook)
+    if name == "ks_theta":
+        c = W.kuramoto(N)
+        return ("ks", lambda m: S.Theta(m, theta=0.5), c["x"], c["fields"], c["pars"], c["dt"],
+                S.null_hook)
+    if name.startswith("burgers"):
+        c = W.burgers(N, int(name[-1]))
+        return (c["model"], lambda m: S.ROS2(m), c["x"], c["fields"], c["pars"], c["dt"],
+                S.null_hook)
+    if name == "advdiff":                     # non-periodic, Dirichlet hook
+        c = W.readme(N)
+        return ("advdiff", lambda m: S.ROS3PRw(m, **FX), c["x"], c["fields"], c["pars"], 0.01,
+                S.Dirichlet(U=(1.0, 0.0)))
+    if name == "advdiff_node":                # periodic, per-node parameter, slow decay
+        x = np.linspace(0, 10, N)
+        U = np.cos(2 * np.pi * x / 10) + 0.1 * rng.standard_normal(N)
+        return ("advdiff", lambda m: S.ROS3PRw(m, **FX), x, dict(U=U),
+                dict(k=1e-2 * (1 + rng.random(N)), c=.3, periodic=True), 0.01, S.null_hook)
+    if name == "heat":                        # periodic, the border fill reaches every tile
+        x = np.linspace(0, 10, N)
+        return ("heat", lambda m: S.ROS3PRw(m, **FX), x, dict(T=np.cos(2 * np.pi * x / 10)),
+                dict(k=1.0, periodic=True), 0.5, S.null_hook)
+    raise KeyError(name)
+
+
+def _grid_run(name, N, steps, mode):
+    from triflow_b200.ensemble import Ensemble
+    mname, mk, x, fields, pars, dt, hook = _grid_case(name, N)
+    m = gmodel(mname)
+    ens = Ensemble(m, mk(m), x, fields, pars, hook=hook, batch=1)
+    ens.set_fusion(mode)
+    launches0 = ens_launches(ens)
+    err = ens.step(dt, steps, want_err=True)
+    n = ens_launches(ens) - launches0
+    u = ens.download()[0].copy()
+    assert not ens.state.status().any()
+    ens.state.close()
+    return u, err, n
+
+
+def ens_launches(ens):
+    from triflow_b200 import _lib
+    return _lib.lib().tf_ctx_launch_count(ens.state.ctx)
+
+
+# every position of the domain end relative to chunk (8), thread (16 nodes) and tile
+# boundaries; one tile and many; periodic and clamped ends; P = 1 and P = 2; every tableau
+# the kernel takes (s <= 3); the border fill reaching no, some and all tiles
+GRID_CASES = [("ks", 1000), ("ks", 2048), ("ks", 2049), ("ks", 2055), ("ks", 2056), ("ks", 2057),
+              ("ks", 4096), ("ks", 16384), ("ks", 50000), ("ks", 123457), ("ks_edge", 30000),
+              ("ks_edge", 513), ("ks_theta", 70001), ("burgers1", 16384), ("burgers2", 65536),
+              ("burgers3", 99999), ("advdiff", 5000), ("advdiff", 20000), ("advdiff_node", 3000),
+              ("heat", 5000), ("heat", 65536), ("ks", 17), ("burgers1", 9)]
+
+
+@pytest.mark.parametrize("name,N", GRID_CASES)
+def test_grid_resident_step_equals_kernel_pipeline(name, N):
+    """tf_k_gridstep (one cooperative launch per step, tiles coupled through tagged words)
+    runs the algorithm of the per-kernel pipeline: same chunk maps, same scans, border block
+    for the periodic corners.  The scan trees differ (two chunks per thread, other tile
+    sizes), so the two agree to rounding, amplified by the dynamics: KS grows a 1e-15
+    perturbation to 3e-12 in one step, hence 5e-10 after 5 steps."""
+    steps = 5
+    ug, eg, ng = _grid_run(name, N, steps, "grid")
+    up, ep, n_pipe = _grid_run(name, N, steps, False)
+    assert np.isfinite(ug).all()
+    assert ng < n_pipe and ng <= 2 * steps + 2         # one launch per step (+ hook launches)
+    assert rel_traj_err(ug, up) <= 5e-10
+    assert np.allclose(eg, ep, rtol=1e-6, atol=1e-300, equal_nan=True)
+
+
+@pytest.mark.parametrize("name,N,steps", [("ks", 4096, 10), ("ks", 2049, 10), ("burgers1", 3000, 20),
+                                          ("heat", 3000, 10), ("advdiff", 3000, 20)])
+def test_grid_resident_step_vs_oracle(name, N, steps):
+    """The same path against the CPU oracle (reference algorithm: numpy compiler + SuperLU)."""
+    from oracle import schemes as O
+    mname, mk, x, fields, pars, dt, hook = _grid_case(name, N)
+    ug, _, _ = _grid_run(name, N, steps, "grid")
+    om = omodel(mname)
+    f = om.fields_template(x=x, **fields)
+    osch = getattr(O, type(mk(gmodel(mname))).__name__)
+    sch = osch(om, **FX) if osch is O.ROS3PRw else osch(om)
+    t = 0.0
+    for _ in range(steps):
+        t, f = sch(t, f, dt, pars, hook=hook)
+    assert rel_traj_err(ug, f.uflat) <= TRAJ_TOL
+
+
+def test_grid_resident_full_size_ks():
+    """BASELINE config 3 at its real size (N = 2^20, where the path is the default): agrees
+    with the per-kernel pipeline, and uses one launch per step."""
+    ug, eg, ng = _grid_run("ks", 1 << 20, 5, True)
+    up, ep, n_pipe = _grid_run("ks", 1 << 20, 5, False)
+    assert ng == 5 and n_pipe > 5 * 5
+    assert rel_traj_err(ug, up) <= 5e-10
+
+
+def test_singular_step_does_not_poison_the_state():
+    """A failed factorisation is reported by the call that hit it and by no later one
+    (every scheme call of the reference is independent)."""
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.ensemble import Ensemble
+    m = gmodel("burgers_up1")               # J depends on the state: a NaN reaches the pivots
+    x = np.arange(512) * 0.2
+    c = dict(x=x, fields=dict(U=np.stack([np.sin(x / 7), np.cos(x / 5)])),
+             pars=dict(k=np.array([0.1, 0.2]), periodic=False), dt=0.1)
+    ens = Ensemble(m, S.Theta(m, theta=1), c["x"], c["fields"], c["pars"], batch=2)
+    u0 = ens.download().copy()
+    bad = u0.copy()
+    bad[1, 100] = np.nan                    # -> non-finite rows -> status bit of member 1
+    ens.upload(bad)
+    with pytest.raises(RuntimeError):
+        ens.step(c["dt"], 1)
+    ens.upload(u0)
+    ens.step(c["dt"], 2)                    # must succeed: the status was cleared
+    assert np.isfinite(ens.download()).all()
+    assert not ens.state.status().any()
+
+
+def test_pivot_growth_is_reported():
+    """The device LU does not pivot (SuperLU does): a pivot 1e13 times smaller than the entry
+    it eliminates gives a useless factor.  It must be reported, on every path, instead of
+    returning a silently wrong state; the reference's pivoting solver handles the system."""
+    from oracle import schemes as O
+    from triflow_b200 import schemes as S
+    from triflow_b200.ensemble import Ensemble
+    N, dt = 300, 0.01
+    x = np.linspace(0, 1, N)
+    dx = (x[-1] - x[0]) / (N - 1)
+    k = -(1 - 1e-13) * dx * dx / dt          # A[0,0] = 1 + dt*k/dx^2 ~ 1e-13, A[1,0] ~ 1
+    pars = dict(k=k, c=0.0, periodic=False)
+    fields = dict(U=np.cos(2 * np.pi * x))
+    gm, om = gmodel("advdiff"), omodel("advdiff")
+    _, fo = O.Theta(om, theta=1)(0.0, om.fields_template(x=x, **fields), dt, pars)
+    assert np.isfinite(fo.uflat).all()
+    for mode in (True, False, "grid"):
+        ens = Ensemble(gm, S.Theta(gm, theta=1), x, fields, pars, batch=1)
+        ens.set_fusion(mode)
+        with pytest.raises(RuntimeError, match="pivot growth"):
+            ens.step(dt, 1)
+        assert ens.state.status()[0] & 8

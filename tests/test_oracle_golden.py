@@ -138,6 +138,21 @@ def test_ensemble_members():
         assert rel_traj_err(snaps[-1], g["ensemble_512_final"][idx]) <= TOL
 
 
+def test_ensemble_members_full_grid():
+    """cfg 5 at N = 4096: the oracle against three of the 64 members the reference ran."""
+    from helpers import traj_ens4096
+    g = traj_ens4096()
+    mem = g["members"]
+    c = W.ensemble(4096, mem)
+    m = omodel("advdiff")
+    for idx in (0, len(mem) // 2, len(mem) - 1):
+        pars = dict(k=float(c["pars"]["k"][idx]), c=float(c["pars"]["c"][idx]),
+                    periodic=False)
+        snaps = run_fixed(m, O.ROS3PRw(m, time_stepping=False), c, 100, 100,
+                          hook=W.readme_hook, pars=pars)
+        assert rel_traj_err(snaps[-1], g["final"][idx]) <= TOL
+
+
 @pytest.mark.parametrize("sname,kw", [("ROS2", {}),
                                       ("ROS3PRw", dict(time_stepping=False)),
                                       ("Theta", {})])

@@ -75,7 +75,7 @@ def make(case, N):
 def run(case, N, steps, fuse, timing=0):
     m, sch, c, hook = make(case, N)
     e = Ensemble(m, sch, c["x"], c["fields"], c["pars"], hook=hook, batch=1)
-    e.set_fusion(fuse)
+    e.set_fusion("grid" if fuse else 0)
     lib, ctx = _lib.lib(), m._cuda.ctx
     e.step(c["dt"], steps)
     e.sync()
@@ -133,6 +133,10 @@ def main():
         check("burgers3", 99999, 5)
         check("advdiff", 5000, 5)
         check("ks", 1 << 20, 10)
+    if mode == "sweep":
+        for case in ("ks", "burgers1"):
+            for e in (10, 12, 14, 16, 17, 18, 19, 20):
+                check(case, 1 << e, 3, timing=20)
     if mode in ("quick", "full", "time"):
         check("ks", 1 << 20, 3, timing=20)
         check("burgers1", 1 << 17, 3, timing=20)

@@ -22,6 +22,7 @@ else:
     c, name, mk, s = W.burgers(N, 1), "burgers_up1", lambda m: S.ROS2(m), 2
 m = Model(**W.model_args(name), compiler="cuda")
 e = Ensemble(m, mk(m), c["x"], c["fields"], c["pars"], batch=1)
+e.set_fusion("grid")
 e.step(c["dt"], 6)
 e.sync()
 buf = np.zeros(256 * 32, dtype=np.uint64)

@@ -37,6 +37,11 @@
 #define TF_UNROLL
 #endif
 
+// largest multiplier |l| = |a / pivot| accepted before the factorisation is reported as failed
+#ifndef TF_GROWTH_LIMIT
+#define TF_GROWTH_LIMIT 1e10
+#endif
+
 // reciprocal of a pivot: correctly rounded, without the IEEE-division slow path
 #ifdef __CUDA_ARCH__
 #define TF_RCP(x) __drcp_rn(x)
@@ -211,7 +216,7 @@ struct ChunkLU {
     // banded LU without pivoting + forward substitution
     TF_UNROLL for (int k = 0; k < C; ++k) {
       const double piv = T[k][BETA];
-      if (!(piv != 0.0) || !(fabs(piv) < 1e300)) bad = 1;
+      if (!(piv != 0.0) || !(fabs(piv) < 1e300)) bad |= 1;
       const double inv = TF_RCP(piv);
       TF_UNROLL for (int r = k + 1; r < C && r <= k + BETA; ++r) {
         const double l = T[r][BETA + k - r] * inv;
@@ -266,7 +271,14 @@ struct ChunkLU {
       TF_UNROLL for (int q = 0; q < BETA; ++q) Lnext[a][q] = 0.0;
     TF_UNROLL for (int k = 0; k < C; ++k) {
       const double piv = T[k][BETA];
-      if (!(piv != 0.0) || !(fabs(piv) < 1e300)) bad = 1;
+      if (!(piv != 0.0) || !(fabs(piv) < 1e300)) bad |= 1;
+      // no pivoting here (SuperLU row-pivots): a pivot far smaller than the entries it
+      // eliminates means multipliers > 1e10 and a useless factor -- say so (status bit 3)
+      {
+        double mx = 0.0;
+        TF_UNROLL for (int r = k + 1; r < RT && r <= k + BETA; ++r) mx = fmax(mx, fabs(T[r][BETA + k - r]));
+        if (fabs(piv) * TF_GROWTH_LIMIT < mx) bad |= 8;
+      }
       const double inv = TF_RCP(piv);
       Uf[k][0] = inv;
       TF_UNROLL for (int c = 1; c <= BETA; ++c) Uf[k][c] = T[k][BETA + c];
@@ -296,7 +308,14 @@ struct ChunkLU {
       TF_UNROLL for (int q = 0; q < BETA; ++q) Lnext[a][q] = 0.0;
     TF_UNROLL for (int k = 0; k < C; ++k) {
       const double piv = T[k][BETA];
-      if (!(piv != 0.0) || !(fabs(piv) < 1e300)) bad = 1;
+      if (!(piv != 0.0) || !(fabs(piv) < 1e300)) bad |= 1;
+      // no pivoting here (SuperLU row-pivots): a pivot far smaller than the entries it
+      // eliminates means multipliers > 1e10 and a useless factor -- say so (status bit 3)
+      {
+        double mx = 0.0;
+        TF_UNROLL for (int r = k + 1; r < RT && r <= k + BETA; ++r) mx = fmax(mx, fabs(T[r][BETA + k - r]));
+        if (fabs(piv) * TF_GROWTH_LIMIT < mx) bad |= 8;
+      }
       const double inv = TF_RCP(piv);
       Uf[k][0] = inv;
       TF_UNROLL for (int c = 1; c <= BETA; ++c) Uf[k][c] = T[k][BETA + c];

@@ -57,7 +57,10 @@ __device__ unsigned long long tf_gs_trace[256 * 32];
 
 namespace tfk {
 
-constexpr int GS_G = 2;                         // chunks per thread
+#ifndef TF_GS_G
+#define TF_GS_G 2
+#endif
+constexpr int GS_G = TF_GS_G;                   // chunks per thread (1 or 2)
 constexpr int GS_NT = TF_GS_NT;
 constexpr int GS_MAXW = GS_NT / 32;
 constexpr int GS_NPH = 1 + 2 * 3;               // look-back phases: factor, (fwd, bwd) x 3 stages
@@ -65,23 +68,24 @@ constexpr int GS_STAGES = 3;
 static_assert(32 % GS_G == 0, "a thread's chunks lie in one warp-block");
 static_assert(C % BETA == 0, "streaming factorisation walks sub-blocks of BETA rows");
 
-// ---- fat affine map of the first forward sweep of a periodic system: the state of the
-//      substitution itself (PhiL, cy), of the NB columns of W = L^-1 E (same propagator PhiL)
-//      and of the NB columns of G^T = F^T U^-1 (forward substitution with U^T in "push" form:
-//      the state is the sum already pushed onto the next BETA rows; propagator PhiG).
+// ---- map of the first forward sweep of a periodic system.  The border fill (W = L^-1 E,
+//      G^T = F^T U^-1) consists of forward recurrences whose right-hand sides are non-zero in the
+//      first NB rows of the system only, so the state entering any later chunk is
+//          (propagators of all chunks in between) x (state leaving the system's first chunk).
+//      The scan therefore carries, beside the substitution itself (PhiL, cy), only the prefix
+//      product of the propagator of the G recurrence (PhiG; forward substitution with U^T in
+//      "push" form: the state is the sum already pushed onto the next BETA rows).  W shares
+//      PhiL.  The first chunk enters with identity propagators: an exclusive prefix never uses
+//      the first element's propagator for its c-part, and the products then start behind it.
 struct AffB {
-  static constexpr int K = 2 * BETA * BETA + BETA + 2 * NB * BETA;
+  static constexpr int K = 2 * BETA * BETA + BETA;
   double d[K];
   __device__ __forceinline__ double* PhiL() { return d; }
   __device__ __forceinline__ double* cy() { return d + BETA * BETA; }
-  __device__ __forceinline__ double* cW() { return d + BETA * BETA + BETA; }                 // [NB][BETA]
-  __device__ __forceinline__ double* PhiG() { return d + BETA * BETA + BETA + NB * BETA; }
-  __device__ __forceinline__ double* cG() { return d + 2 * BETA * BETA + BETA + NB * BETA; }  // [NB][BETA]
+  __device__ __forceinline__ double* PhiG() { return d + BETA * BETA + BETA; }
   __device__ __forceinline__ const double* PhiL() const { return d; }
   __device__ __forceinline__ const double* cy() const { return d + BETA * BETA; }
-  __device__ __forceinline__ const double* cW() const { return d + BETA * BETA + BETA; }
-  __device__ __forceinline__ const double* PhiG() const { return d + BETA * BETA + BETA + NB * BETA; }
-  __device__ __forceinline__ const double* cG() const { return d + 2 * BETA * BETA + BETA + NB * BETA; }
+  __device__ __forceinline__ const double* PhiG() const { return d + BETA * BETA + BETA; }
   __device__ static __forceinline__ AffB identity() {
     AffB m;
 #pragma unroll
@@ -101,17 +105,6 @@ struct AffB {
 #pragma unroll
       for (int k = 0; k < BETA; ++k) sy += b.PhiL()[i * BETA + k] * a.cy()[k];
       o.cy()[i] = sy;
-#pragma unroll
-      for (int c = 0; c < NB; ++c) {
-        double sw = b.cW()[c * BETA + i], sg = b.cG()[c * BETA + i];
-#pragma unroll
-        for (int k = 0; k < BETA; ++k) {
-          sw += b.PhiL()[i * BETA + k] * a.cW()[c * BETA + k];
-          sg += b.PhiG()[i * BETA + k] * a.cG()[c * BETA + k];
-        }
-        o.cW()[c * BETA + i] = sw;
-        o.cG()[c * BETA + i] = sg;
-      }
     }
     return o;
   }
@@ -148,12 +141,12 @@ struct GsRec {
   __device__ __forceinline__ long long o_misc() const { return o_spart() + (long long)tiles * NB * NB; }
   __device__ __forceinline__ LbWord* xb(int stage) const { return base + o_misc() + stage * NB; }
   __device__ __forceinline__ LbWord* ftop() const { return base + o_misc() + GS_STAGES * NB; }
-  __device__ __forceinline__ long long o_err() const { return o_misc() + GS_STAGES * NB + NB * NB; }
+  __device__ __forceinline__ LbWord* w0() const { return base + o_misc() + GS_STAGES * NB + NB * NB; }   // [2][NB][BETA]
+  __device__ __forceinline__ long long o_err() const { return o_misc() + GS_STAGES * NB + NB * NB + 2 * NB * BETA; }
   __device__ __forceinline__ double* errt() const { return (double*)(base + o_err()); }   // [tiles] doubles
 };
 // (the host side mirrors the size of this area in tf_host.cu: gs_words)
 
-constexpr int GS_MAXTILES = 160;
 struct GsShared {
   double scan[(GS_MAXW + 2) * GS_KMAX];   // warp totals, [GS_MAXW]: tile prefix
   double cst[NC2];
@@ -165,8 +158,9 @@ struct GsShared {
   double sinv[NB * NB];
   double ftop[NB * NB];                // periodic corner block F_top (lives with the border rows)
   double err[GS_MAXW];
-  int alist[GS_MAXTILES];              // last tile: the other tiles whose rows of W / G are non-zero
-  int nalive;
+  double gbot[NB * NB];                // last tile: G of the last NB interior rows [row][col]
+  double sbot[NB * NB];                // last tile: G^T W over those rows
+  int nalive;                          // last tile: leading tiles whose rows of W / G are non-zero
   int epoch;
   volatile int abort;
 };
@@ -271,7 +265,7 @@ __device__ __noinline__ Mon gs_lookback(const Mon& aggregate, GsCtx& cx, int ph,
 // ---- exclusive prefix of every thread's element over (thread, tile) order, or the mirrored
 //      order (REV: backward substitution).  Warp shuffles -> shared memory -> look-back.
 template <class Mon, bool REV>
-__device__ __noinline__ Mon gs_scan(const Mon& mine, GsCtx& cx, int ph) {
+__device__ __forceinline__ Mon gs_scan(const Mon& mine, GsCtx& cx, int ph) {
   double* smem = cx.sh->scan;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = cx.T >> 5;
   const int ml = REV ? 31 - lane : lane;
@@ -417,7 +411,7 @@ __device__ __noinline__ void gs_factor_pass1(const Geom& g, const Buf& b, int ch
   }
 #pragma unroll
   for (int q = 0; q < Star::K; ++q)
-    if (!(fabs(mine.d[q]) < 1e300)) bad = 1;
+    if (!(fabs(mine.d[q]) < 1e300)) bad |= 1;
   out = mine;
 }
 
@@ -508,10 +502,13 @@ __device__ __forceinline__ void gs_factor(const Geom& g, const Buf& b, GsCtx& cx
   int bad = 0;
   Star mine = Star::identity();
   if (th.active) {
-    Star m0, m1;
-    gs_factor_pass1(g, b, th.chunk0, a, sh.cst, m0, bad);
-    gs_factor_pass1(g, b, th.chunk0 + 1, a, sh.cst, m1, bad);
-    mine = Star::combine(m0, m1);
+    gs_factor_pass1(g, b, th.chunk0, a, sh.cst, mine, bad);
+#pragma unroll 1
+    for (int h = 1; h < GS_G; ++h) {
+      Star m1;
+      gs_factor_pass1(g, b, th.chunk0 + h, a, sh.cst, m1, bad);
+      mine = Star::combine(mine, m1);
+    }
   }
   GS_STAMP(1);
   const Star pre = gs_scan<Star, false>(mine, cx, 0);
@@ -544,7 +541,7 @@ __device__ __forceinline__ void gs_factor(const Geom& g, const Buf& b, GsCtx& cx
           for (int q = r + 1; q <= BETA; ++q) gs_post(cx, cx.rec.lnext(cx.tile) + r * BETA + q - 1, Lout[r][q - 1]);
       }
     }
-    if (bad) atomicOr(cx.status, 1);
+    if (bad) atomicOr(cx.status, bad);
   }
   // first rows of the tile: multipliers with respect to the previous tile's pivots
   if (th.t == 0) {
@@ -634,7 +631,7 @@ __device__ __forceinline__ void gs_gw_partial(const Geom& g, const Buf& b, GsCtx
   __syncthreads();
 }
 
-// Sum over the alive tiles (sh.alist) of `per` words each, in list order, added to
+// Sum over the alive tiles (0 .. sh.nalive-1) of `per` words each, in tile order, added to
 // sh.red[0][0 .. per).  All threads of the (last) tile take part; one memory round trip per
 // 32 tiles.
 template <int KIND>   // 0: spart words, 1: gpart words of stage `which`
@@ -643,8 +640,8 @@ __device__ __noinline__ void gs_gather_sum(GsCtx& cx, int which, int per, int si
   for (int base = 0; base < sh.nalive; base += 32) {
     const int n = sh.nalive - base < 32 ? sh.nalive - base : 32;
     for (int idx = threadIdx.x; idx < n * per; idx += cx.T)
-      sh.gather[idx] = gs_wait(cx, (KIND == 0 ? cx.rec.spart(sh.alist[base + idx / per])
-                                              : cx.rec.gpart(which, sh.alist[base + idx / per])) + idx % per, site);
+      sh.gather[idx] = gs_wait(cx, (KIND == 0 ? cx.rec.spart(base + idx / per)
+                                              : cx.rec.gpart(which, base + idx / per)) + idx % per, site);
     __syncthreads();
     if ((int)threadIdx.x < per) {
       double v = sh.red[0][threadIdx.x];
@@ -655,19 +652,17 @@ __device__ __noinline__ void gs_gather_sum(GsCtx& cx, int which, int per, int si
   }
 }
 
-// Last tile, once per step: which other tiles have non-zero rows of W / G; the bottom rows of
-// W and G (natural coupling of the last NB interior rows to the border, superposed on what
-// the fill left there); S = (I - a Ab) - G^T W and its inverse.
-__device__ __noinline__ void gs_border_last(const Geom& g, const Buf& b, GsCtx& cx, const GsThread& th,
-                                            double a, const double* sL, bool th_alive) {
+// Last tile, right after the factorisation: the bottom rows of W and G (natural coupling of the
+// last NB interior rows to the border block; a local NB-row solve) and their share of G^T W.
+// The fill of a periodic system is added onto these rows later, if it reaches them at all.
+__device__ __noinline__ void gs_border_bottom(const Geom& g, const Buf& b, GsCtx& cx, double a,
+                                              const double* sL) {
   GsShared& sh = *cx.sh;
   const int TR = cx.T * GS_G * C;
   const int row0 = cx.tile * TR;
   const int bot0 = g.nhat - NB;
   const double* bt = b.btab;
-  // alive flags of the other tiles (parallel polls), compacted in tile order
-  for (int t = threadIdx.x; t < cx.tiles - 1; t += cx.T)
-    sh.alist[t] = (g.periodic && gs_wait(cx, cx.rec.alive(t), 6) != 0.0) ? 1 : 0;
+  __shared__ double s_wbot[NB * NB];
   if (threadIdx.x < 2 * NB) {
     const bool isW = threadIdx.x < NB;
     const int c = isW ? threadIdx.x : threadIdx.x - NB;
@@ -684,18 +679,47 @@ __device__ __noinline__ void gs_border_last(const Geom& g, const Buf& b, GsCtx& 
       }
       loc[j] = v;
       const double out = isW ? v : v * b.Uf[fidx(gr, 0, BETA + 1)];
-      double* dst = (isW ? b.Wb : b.Gb) + fidx(gr, c, NB);
-      *dst = *dst + out;               // (rows the fill did not reach were zeroed by their owner)
+      ((isW ? b.Wb : b.Gb) + fidx(gr, c, NB))[0] = out;
+      (isW ? s_wbot : sh.gbot)[j * NB + c] = out;
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int na = 0;
-    for (int t = 0; t < cx.tiles - 1; ++t)
-      if (sh.alist[t]) sh.alist[na++] = t;
-    sh.nalive = na;
+  if (threadIdx.x < NB * NB) {
+    const int i = threadIdx.x / NB, j = threadIdx.x % NB;
+    double v = 0.0;
+    for (int r = 0; r < NB; ++r) v = __fma_rn(sh.gbot[r * NB + i], s_wbot[r * NB + j], v);
+    sh.sbot[threadIdx.x] = v;
   }
-  gs_gw_partial(g, b, cx, th, th_alive, true);               // own rows -> sh.red[0]
+  __syncthreads();
+}
+
+// Last tile, after the first forward scan: how many leading tiles have non-zero rows of W / G,
+// S = (I - a Ab) - G^T W and its inverse.  own_alive: the fill reached this tile too.
+__device__ __noinline__ void gs_border_finish(const Geom& g, const Buf& b, GsCtx& cx, const GsThread& th,
+                                              double a, bool th_alive, bool own_alive) {
+  GsShared& sh = *cx.sh;
+  const double* bt = b.btab;
+  // the alive tiles are a prefix (a state that has become exactly zero stays zero)
+  if (threadIdx.x < 32) {
+    int na = 0;
+    if (g.periodic) {
+      for (int base = 0; base < cx.tiles - 1; base += 32) {
+        const int t = base + (int)threadIdx.x;
+        const bool al = (t < cx.tiles - 1) && gs_wait(cx, cx.rec.alive(t), 6) != 0.0;
+        const unsigned m = __ballot_sync(0xffffffffu, al);
+        const int lead = (~m == 0u) ? 32 : (__ffs(~m) - 1);
+        na += lead;
+        if (lead < 32) break;
+      }
+    }
+    if (threadIdx.x == 0) sh.nalive = na;
+  }
+  if (own_alive) {
+    gs_gw_partial(g, b, cx, th, th_alive, true);             // own rows incl. the bottom ones
+  } else {
+    if (threadIdx.x < NB * NB) sh.red[0][threadIdx.x] = sh.sbot[threadIdx.x];
+    __syncthreads();
+  }
   gs_gather_sum<0>(cx, 0, NB * NB, 7);
   if (threadIdx.x == 0) {
     double S[NB * NB], I[NB * NB];
@@ -797,8 +821,8 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
     __syncthreads();
     double rhs_all[GS_G][C];
     Aff mh[GS_G];
-    mh[0] = Aff::identity();
-    mh[1] = Aff::identity();
+#pragma unroll
+    for (int h = 0; h < GS_G; ++h) mh[h] = Aff::identity();
     if (th.active) {
 #pragma unroll
       for (int h = 0; h < GS_G; ++h) {
@@ -853,7 +877,6 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
       for (int t = 0; t < BETA; ++t) { ws[c][t] = 0.0; pg[c][t] = 0.0; }
     const bool first_chunk = (cx.tile == 0 && th.t == 0);
     if (I == 0 && g.periodic) {
-      // fat map: the substitution + the NB columns of W + the NB columns of G
       AffB mb[GS_G];
 #pragma unroll
       for (int h = 0; h < GS_G; ++h) {
@@ -863,41 +886,82 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
 #pragma unroll
         for (int k = 0; k < BETA; ++k) mb[h].cy()[k] = mh[h].c()[k];
       }
+      double w0[2][NB][BETA];               // states leaving the system's first chunk
       if (first_chunk && th.active) {
-        // particular solutions of the system's first chunk (zero incoming state)
         const double* Ug = b.Uf + th.cb(0) * (BETA + 1) - (long long)(th.cl) * BETA;
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
-          double s[BETA], p[BETA];
+          double sW[BETA], p[BETA];
 #pragma unroll
-          for (int t = 0; t < BETA; ++t) { s[t] = 0.0; p[t] = 0.0; }
+          for (int t = 0; t < BETA; ++t) { sW[t] = 0.0; p[t] = 0.0; }
 #pragma unroll
           for (int r = 0; r < C; ++r) {
             double v = gs_fw(b.btab, a, r, c);
 #pragma unroll
-            for (int q = 0; q < BETA; ++q) v -= sL[gs_sl(r, q, 0, 0, T)] * s[q];
+            for (int q = 0; q < BETA; ++q) v -= sL[gs_sl(r, q, 0, 0, T)] * sW[q];
 #pragma unroll
-            for (int q = BETA - 1; q > 0; --q) s[q] = s[q - 1];
-            s[0] = v;
+            for (int q = BETA - 1; q > 0; --q) sW[q] = sW[q - 1];
+            sW[0] = v;
             const double gv = (gs_fg(sh.ftop, a, r, c) - p[0]) * Ug[(long long)(r * (BETA + 1)) * 32];
 #pragma unroll
             for (int t = 0; t < BETA; ++t)
               p[t] = ((t + 1 < BETA) ? p[t + 1 < BETA ? t + 1 : 0] : 0.0) + Ug[(long long)(r * (BETA + 1) + t + 1) * 32] * gv;
           }
 #pragma unroll
-          for (int t = 0; t < BETA; ++t) { mb[0].cW()[c * BETA + t] = s[t]; mb[0].cG()[c * BETA + t] = p[t]; }
+          for (int t = 0; t < BETA; ++t) {
+            w0[0][c][t] = sW[t];
+            w0[1][c][t] = p[t];
+            gs_post(cx, cx.rec.w0() + c * BETA + t, sW[t]);
+            gs_post(cx, cx.rec.w0() + (NB + c) * BETA + t, p[t]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < BETA * BETA; ++k) {      // the products start behind the first chunk
+          mb[0].PhiL()[k] = (k / BETA == k % BETA) ? 1.0 : 0.0;
+          mb[0].PhiG()[k] = (k / BETA == k % BETA) ? 1.0 : 0.0;
         }
       }
-      const AffB mineB = AffB::combine(mb[0], mb[1]);
+      AffB mineB = mb[0];
+#pragma unroll
+      for (int h = 1; h < GS_G; ++h) mineB = AffB::combine(mineB, mb[h]);
       const AffB pre = gs_scan<AffB, false>(mineB, cx, 1);
 #pragma unroll
       for (int t = 0; t < BETA; ++t) sv[t] = pre.cy()[t];
+      if (first_chunk) {
+        if (th.active) {
+          // (chunk 0 itself starts from zero; its rows are redone below with the rhs)
+        }
+      } else if (th.active) {
+        bool nz = false;
 #pragma unroll
-      for (int c = 0; c < NB; ++c)
+        for (int k = 0; k < BETA * BETA; ++k) nz = nz || (pre.PhiL()[k] != 0.0) || (pre.PhiG()[k] != 0.0);
+        if (nz) {
 #pragma unroll
-        for (int t = 0; t < BETA; ++t) { ws[c][t] = pre.cW()[c * BETA + t]; pg[c][t] = pre.cG()[c * BETA + t]; }
+          for (int c = 0; c < NB; ++c) {
+            double vW[BETA], vG[BETA];
+#pragma unroll
+            for (int t = 0; t < BETA; ++t) {
+              vW[t] = gs_wait(cx, cx.rec.w0() + c * BETA + t, 13);
+              vG[t] = gs_wait(cx, cx.rec.w0() + (NB + c) * BETA + t, 13);
+            }
+#pragma unroll
+            for (int i = 0; i < BETA; ++i) {
+              double sw = 0.0, sg = 0.0;
+#pragma unroll
+              for (int k = 0; k < BETA; ++k) {
+                sw += pre.PhiL()[i * BETA + k] * vW[k];
+                sg += pre.PhiG()[i * BETA + k] * vG[k];
+              }
+              ws[c][i] = sw;
+              pg[c][i] = sg;
+            }
+          }
+        }
+      }
     } else {
-      const Aff mine = Aff::combine(mh[0], mh[1]);
+      Aff mine = mh[0];
+#pragma unroll
+      for (int h = 1; h < GS_G; ++h) mine = Aff::combine(mine, mh[h]);
       const Aff pre = gs_scan<Aff, false>(mine, cx, 1 + 2 * I);
 #pragma unroll
       for (int t = 0; t < BETA; ++t) sv[t] = pre.c()[t];
@@ -948,35 +1012,21 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
 #pragma unroll
                 for (int q = BETA - 1; q > 0; --q) ws[c][q] = ws[c][q - 1];
                 ws[c][0] = v;
-                b.Wb[o + (long long)c * 32] = v;
+                const bool onb = gr >= bot0 && gr < g.nhat;      // bottom rows: already hold their local part
+                b.Wb[o + (long long)c * 32] = onb ? b.Wb[o + (long long)c * 32] + v : v;
                 const double gv = (gs_fg(sh.ftop, a, gr, c) - pg[c][0]) * inv;
 #pragma unroll
                 for (int t = 0; t < BETA; ++t)
                   pg[c][t] = ((t + 1 < BETA) ? pg[c][t + 1 < BETA ? t + 1 : 0] : 0.0) + uq[t] * gv;
-                b.Gb[o + (long long)c * 32] = gv;
+                b.Gb[o + (long long)c * 32] = onb ? b.Gb[o + (long long)c * 32] + gv : gv;
               }
             }
           }
         }
       }
-      // bottom rows the fill did not reach start from zero (gs_border_last adds onto them)
-      if (last_tile && th.active && !th_alive) {
-#pragma unroll
-        for (int h = 0; h < GS_G; ++h) {
-          const int r0 = (th.chunk0 + h) * C;
-          if (r0 + C > bot0 && r0 < g.nhat) {
-#pragma unroll
-            for (int r = 0; r < C; ++r)
-              if (r0 + r >= bot0 && r0 + r < g.nhat) {
-#pragma unroll
-                for (int c = 0; c < NB; ++c) { b.Wb[fidx(r0 + r, c, NB)] = 0.0; b.Gb[fidx(r0 + r, c, NB)] = 0.0; }
-              }
-          }
-        }
-      }
       tile_alive = __syncthreads_or(th_alive ? 1 : 0) != 0;
       if (last_tile) {
-        gs_border_last(g, b, cx, th, a, sL, th_alive);
+        gs_border_finish(g, b, cx, th, a, th_alive, tile_alive);
       } else {
         if (threadIdx.x == 0) gs_post(cx, cx.rec.alive(cx.tile), tile_alive ? 1.0 : 0.0);
         if (tile_alive) {
@@ -1046,7 +1096,8 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
         for (int c = 0; c < NB; ++c) acc[c] = sh.red[0][c];
         for (int j = 0; j < NB; ++j) {                        // natural coupling of the last rows
           const int gr = bot0 + j;
-          for (int c = 0; c < NB; ++c) acc[c] = __fma_rn(b.Gb[fidx(gr, c, NB)], sh.yb[j], acc[c]);
+          for (int c = 0; c < NB; ++c)
+            acc[c] = __fma_rn(tile_alive ? b.Gb[fidx(gr, c, NB)] : sh.gbot[j * NB + c], sh.yb[j], acc[c]);
         }
         double ybv[NB];
         for (int c = 0; c < NB; ++c) ybv[c] = __dsub_rn(sh.yb[NB + c], acc[c]);
@@ -1105,7 +1156,9 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
       }
       rs.to_map(mh[h]);
     }
-    mine = Aff::combine(mh[GS_G - 1], mh[0]);           // mirrored order: the later chunk first
+    mine = mh[GS_G - 1];                                 // mirrored order: the later chunk first
+#pragma unroll
+    for (int h = GS_G - 2; h >= 0; --h) mine = Aff::combine(mine, mh[h]);
   }
   GS_STAMP(7 + 6 * I);
   const Aff pre = gs_scan<Aff, true>(mine, cx, 2 + 2 * I);
@@ -1117,7 +1170,6 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
 #pragma unroll
     for (int h = GS_G - 1; h >= 0; --h) {
       const double* Ug = b.Uf + th.cb(h) * (BETA + 1) - (long long)(th.cl + h) * BETA;
-      const int i0 = (th.chunk0 + h) * M;
 #pragma unroll
       for (int r = C - 1; r >= 0; --r) {
         double v = y[h][r];
@@ -1137,22 +1189,6 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
         }
         if (!LAST) {
           b.K[I][aidx] = k;
-          // stage state of the next stage at the tile edges (and the last P real nodes)
-          const int i = i0 + r;
-          const int loc = i - cx.tile * TN;
-          const bool e0 = loc < P, e1 = loc >= TN - P, e2 = last_tile && i >= g.N - P && i < g.N;
-          if (cx.tiles > 1 && (e0 || e1 || e2)) {
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q <= I; ++q) {
-              const double term = __dmul_rn(sd.alpha[I + 1][q], q < I ? kprev[q < I ? q : 0] : k);
-              acc = (q == 0) ? term : __dadd_rn(acc, term);
-            }
-            const double nv = __dadd_rn(b.U[aidx], acc);
-            if (e0) gs_post(cx, cx.rec.halo(I + 1, cx.tile, 0) + loc, nv);
-            if (e1) gs_post(cx, cx.rec.halo(I + 1, cx.tile, 1) + (loc - (TN - P)), nv);
-            if (e2) gs_post(cx, cx.rec.halo(I + 1, cx.tile, 2) + (i - (g.N - P)), nv);
-          }
         } else {
           double acc = 0.0, accp = 0.0;
 #pragma unroll
@@ -1173,13 +1209,49 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
       }
     }
   }
+  if (!LAST && cx.tiles > 1 && th.active) {
+    // stage state of the next stage at the tile edges (and at the last P real nodes) for the
+    // neighbouring tiles; out of the hot loop: only the threads at the edges take this path
+#pragma unroll
+    for (int h = 0; h < GS_G; ++h) {
+      const int i0 = (th.chunk0 + h) * M;
+      const bool first = th.t == 0 && h == 0, lastc = th.t == T - 1 && h == GS_G - 1;
+      const bool tail = last_tile && i0 + M > g.N - P && i0 < g.N;
+      if (first || lastc || tail) {
+#pragma unroll 1
+        for (int r = 0; r < C; ++r) {
+          const int i = i0 + r;
+          const int loc = i - cx.tile * TN;
+          const bool e0 = loc < P, e1 = loc >= TN - P, e2 = last_tile && i >= g.N - P && i < g.N;
+          if (e0 || e1 || e2) {
+            const long long aidx = th.cb(h) + (long long)r * 32;
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q <= I; ++q) {
+              const double term = __dmul_rn(sd.alpha[I + 1][q], b.K[q][aidx]);
+              acc = (q == 0) ? term : __dadd_rn(acc, term);
+            }
+            const double nv = __dadd_rn(b.U[aidx], acc);
+            if (e0) gs_post(cx, cx.rec.halo(I + 1, cx.tile, 0) + loc, nv);
+            if (e1) gs_post(cx, cx.rec.halo(I + 1, cx.tile, 1) + (loc - (TN - P)), nv);
+            if (e2) gs_post(cx, cx.rec.halo(I + 1, cx.tile, 2) + (i - (g.N - P)), nv);
+          }
+        }
+      }
+    }
+  }
   if (!LAST) __syncthreads();       // k_I of the tile is in place before the next stage reads it
   GS_STAMP(9 + 6 * I);
 }
 
 }  // namespace tfk
 
-extern "C" __global__ void __launch_bounds__(tfk::GS_NT, 1) tf_k_gridstep(tfk::Geom g, tfk::Buf b,
+#ifndef TF_GS_MINB
+#define TF_GS_MINB 1
+#endif
+// (read by the host: chunks per thread, max threads per CTA)
+extern "C" __device__ int tf_gs_cfg[2] = {TF_GS_G, TF_GS_NT};
+extern "C" __global__ void __launch_bounds__(tfk::GS_NT, TF_GS_MINB) tf_k_gridstep(tfk::Geom g, tfk::Buf b,
                                                                           TfStepDesc sd) {
   using namespace tfk;
   extern __shared__ __align__(128) double dsm_gs[];
@@ -1214,6 +1286,7 @@ extern "C" __global__ void __launch_bounds__(tfk::GS_NT, 1) tf_k_gridstep(tfk::G
   GS_STAMP(0);
   double phiG[GS_G][BETA * BETA];
   gs_factor(g, b, cx, th, a, sL, phiG);
+  if (cx.tile == cx.tiles - 1) gs_border_bottom(g, b, cx, a, sL);
   double emax = 0.0;
   bool th_alive = false, tile_alive = false;
   switch (sd.s) {

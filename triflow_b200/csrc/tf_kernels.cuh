@@ -799,7 +799,7 @@ __device__ __forceinline__ void factor_body_rows(const Geom& g, const Buf& b, do
         for (int q = r + 1; q <= BETA; ++q)
           Lg[((long long)nb * C + r) * 32 * BETA + (q - 1) * 32 + nl] = Lnext[r][q - 1];
     }
-    if (bad) atomicOr(b.status + sys, 1);
+    if (bad) atomicOr(b.status + sys, bad);
   }
   finish_chain(g, b, epoch);
 }
@@ -928,7 +928,7 @@ __device__ __forceinline__ void factor_body_stream(const Geom& g, const Buf& b, 
     }
 #pragma unroll
     for (int q = 0; q < Star::K; ++q)
-      if (!(fabs(mine.d[q]) < 1e300)) bad = 1;
+      if (!(fabs(mine.d[q]) < 1e300)) bad |= 1;
   }
   const Star pre = tile_scan<Star>(mine, smem, g.tiles > 1, b, (long long)sys * g.tiles, tile,
                                    epoch, Star::identity(), nullptr);
@@ -996,7 +996,7 @@ __device__ __forceinline__ void factor_body_stream(const Geom& g, const Buf& b, 
         for (int q = r + 1; q <= BETA; ++q)
           Lg[((long long)nb * C + r) * 32 * BETA + (q - 1) * 32 + nl] = Lprev[r][q - 1];
     }
-    if (bad) atomicOr(b.status + sys, 1);
+    if (bad) atomicOr(b.status + sys, bad);
   }
   finish_chain(g, b, epoch);
 }

@@ -248,7 +248,7 @@ __device__ __forceinline__ void sys_factor(const Geom& g, const Buf& lb, int sys
     }
 #pragma unroll
     for (int q = 0; q < Star::K; ++q)
-      if (!(fabs(mine.d[q]) < 1e300)) bad = 1;
+      if (!(fabs(mine.d[q]) < 1e300)) bad |= 1;
   }
   SYS_CLK(6);                                            // factor pass 1
   const Star pre = cta_scan<Star, false>(mine, sh.scan, 0);
@@ -775,7 +775,7 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
     SYS_CLK(0);                                          // wait for U (TMA) + constants
     sys_factor(g, lb, sys, a, sh.cst, sh, Lr, Ur, bad);
     SYS_CLK(1);
-    if (bad) atomicOr(b.status + sys, 1);
+    if (bad) atomicOr(b.status + sys, bad);
     SYS_CLK(2);
     double emax = 0.0;
     if constexpr (LONG_TABLEAU) {

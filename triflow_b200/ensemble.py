@@ -57,9 +57,13 @@ class Ensemble:
         self.t = 0.0
 
     def set_fusion(self, enable):
-        """System-resident stepping (one launch per step, state and factor kept on the SM)
-        on / off; off selects the per-kernel pipeline (same algorithm, agrees to rounding)."""
-        _lib.check(_lib.lib().tf_state_set_fusion(self.state.h, 2 if enable == "rt" else int(bool(enable))))
+        """Which step kernels may be used: ``True`` / ``1`` automatic (system-resident kernel
+        when a system fits one CTA, grid-resident single-launch step where it pays), ``False``
+        / ``0`` the per-kernel pipeline only, ``"rt"`` the run-time-stage variant of the
+        system-resident kernel, ``"grid"`` the grid-resident step wherever it applies.  All
+        paths run the same algorithm and agree to rounding."""
+        mode = {"rt": 2, "grid": 3}.get(enable, int(bool(enable)))
+        _lib.check(_lib.lib().tf_state_set_fusion(self.state.h, mode))
 
     def upload(self, u):
         """``u``: (batch, N*nvar) in uflat layout."""
