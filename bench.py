@@ -3,14 +3,16 @@
 implicit grid-point*steps/s; F+J+solve fraction of the HBM roofline).
 
     python bench.py --gpus N --steps K --warmup W [--workload ensemble|ks|burgers|film]
-    python bench.py --impl reference ...        # CPU arm: the oracle port on host cores
+    python bench.py --impl reference ...        # CPU arm: the reference's own numpy + SuperLU path
 
 One "step" is one internal implicit step (one J build + factorisation + s stage
 solves + update) of every system in the batch.  Inputs are synthetic
  and resident in HBM when the timed region starts; the timed
 region is bracketed by a barrier + stream synchronisation and timed with CUDA
 events on the launching stream, max over ranks.  Ensembles are sharded by member
-with no data-path collective (weak scaling: a fixed number of members per GPU).
+with no data-path collective: the BASELINE config (32768 members in total) is split
+contiguously over the ranks (strong scaling); the final gather of the states to rank 0
+is timed separately (``final_gather``).
 """
 
 import argparse
@@ -128,6 +130,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+def make_config(args, wk, mname, N, total_systems, dt, ws):
+    """`config` of the JSON line: identical for the GPU arm and for --impl reference."""
+    units = float(N) * total_systems
+    return {"workload": "%s: %s" % (wk["cfg"], args.workload),
+            "pde": mname, "scheme": wk["scheme"], "nodes": int(N),
+            "systems": int(total_systems), "dt": dt, "fixed_step": True,
+            "parallelism": ("members sharded x%d, no data-path collective, final gather" % ws
+                            if args.workload == "ensemble" else "replicas x%d" % ws),
+            "l2": "working set %.0f MB > 126 MB L2" % (units * wk["Q"] / 1e6)
+            if units * wk["Q"] > 126e6 * ws else
+            "working set %.0f MB fits L2; no flush (steps are dependent)" % (units * wk["Q"] / 1e6)}
+
+
+def bind_near_gpu(index):
+    """Pin this process to the CPU cores NVML reports as close to the GPU, BEFORE any pinned
+    buffer is allocated (first touch then lands on the near NUMA node).  Returns a note."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        cores = [c for c in cores if c < ncpu]
+        if cores:
+            os.sched_setaffinity(0, cores)
+            return "bound to %d cores near GPU %d (%d..%d)" % (len(cores), index, cores[0], cores[-1])
+    except Exception as e:  # noqa: BLE001
+        return "not bound (%s)" % type(e).__name__
+    return "not bound"
+
+
 # ----------------------------------------------------------------- workloads
 def build_problem(name, members, N=None):
     """Returns (model_name, scheme factory, x, fields, pars, hook, batch, N, dt)."""
@@ -158,11 +192,12 @@ def run_gpu(args):
 
     rank, ws = D.init()
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    affinity = bind_near_gpu(local)
     wk = WORKLOADS[args.workload]
     if args.workload == "ensemble":
-        per_gpu = args.members
-        lo = rank * per_gpu                     # weak scaling: per-GPU members fixed
-        members = (np.arange(lo, lo + per_gpu)) % (W.ENSEMBLE_K * W.ENSEMBLE_C)
+        # BASELINE cfg 5: `--members` runs IN TOTAL, contiguous block per rank (strong scaling)
+        lo, hi = D.shard(args.members, rank, ws)
+        members = np.arange(lo, hi) % (W.ENSEMBLE_K * W.ENSEMBLE_C)
     else:
         members = None                          # replicas only
     mname, mk_scheme, x, fields, pars, hook, batch, N, dt = build_problem(
@@ -212,30 +247,53 @@ def run_gpu(args):
     peak, peak_src = peaks()
     achieved = kernel_bytes(wk, dom) * units / (dom_ms / dom_n * 1e-3) / 1e9
     step_gbs = wk["Q"] * units * args.steps / (ms.value * 1e-3) / 1e9
-    traffic, fp64_frac = None, None             # DRAM bytes per launch of that kernel (ncu capture)
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            per_node = json.load(f).get(args.workload, {}).get(dom)
-            fp64_frac = json.load(open(tpath)).get("_fp64_pipe_frac", {}).get(dom)
-        if per_node:
-            traffic = per_node * units          # DRAM bytes per launch (ncu, profiled kernel)
-    roofline = {"bound": "hbm", "kernel": "tf_k_" + dom, "achieved": round(achieved, 1),
+    # Per-launch figures that only a profiler can give (DRAM bytes, fp64 instruction counts)
+    # are STATIC: taken from the committed ncu capture named in `static_source`, scaled by the
+    # nodes of this run -- not measured in this process.
+    static, spath = {}, os.path.join(ROOT, "profiles", "r2_static.json")
+    if os.path.exists(spath):
+        with open(spath) as f:
+            static = json.load(f)
+    sk = static.get(args.workload, {}).get(dom, {})
+    traffic = sk.get("dram_bytes_per_node") and sk["dram_bytes_per_node"] * units
+    roofline = {"bound": sk.get("bound", "hbm"), "kernel": "tf_k_" + dom, "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic,
+                "traffic_source": ("static ncu capture: " + sk["source"]) if traffic else None,
+                "peak_source": peak_src,
                 "kernel_share_of_step": round(dom_ms / tot_ms, 3),
                 "step_achieved": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4),
                 "bytes_per_node_step": wk["Q"],
                 "family_ms_per_step": {k: round(v[0] / psteps, 4) for k, v in fam.items()}}
-    if fp64_frac is not None:
-        roofline["fp64_pipe_frac"] = fp64_frac  # ncu sm__inst_executed_pipe_fp64 (same capture)
-    if dom == "sysstep":
-        # the whole step is one launch that keeps the factor and the stage vectors on the SM:
-        # DRAM traffic is ~16 B/node (traffic), far below the algorithmic Q the roofline is
-        # quoted on, so the kernel is bound by the fp64 pipe / issue rate, not by HBM
-        roofline["note"] = ("system-resident step: achieved = algorithmic Q bytes / time; measured "
-                            "DRAM traffic is ~1/14 of Q, the kernel is fp64-pipe / issue bound "
-                            "(profiles/README.md)")
+    # fp64 pipe: measured peak of this device (DFMA / s, a probe kernel in the library) against
+    # the fp64 operations the kernel executes per node and step (static, same capture)
+    dfma_peak = ctypes.c_double()
+    _lib.check(lib.tf_ctx_fp64_peak(ctx, ctypes.byref(dfma_peak)))
+    roofline["fp64_peak_dfma_per_s"] = dfma_peak.value
+    if sk.get("fp64_inst_per_node_step"):
+        rate = sk["fp64_inst_per_node_step"] * units / (dom_ms / dom_n * 1e-3)
+        roofline["fp64"] = {"achieved_inst_per_s": rate, "peak_inst_per_s": dfma_peak.value,
+                            "frac": round(rate / dfma_peak.value, 4),
+                            "inst_per_node_step": sk["fp64_inst_per_node_step"],
+                            "source": "static ncu capture: " + sk["source"]}
+    if roofline["bound"] != "hbm":
+        roofline["note"] = ("achieved / frac quote the ALGORITHMIC bytes of SURVEY 8d (Q) over the "
+                            "kernel time against the HBM peak, as BASELINE.json asks; this kernel "
+                            "keeps the factor and the stage vectors on the SM, its DRAM traffic is "
+                            "`traffic`, and what bounds it is the fp64 pipe / issue rate (`fp64`)")
+
+    # -- final gather of the states to rank 0 (the only inter-GPU traffic of an ensemble)
+    D.barrier()
+    t0 = time.perf_counter()
+    u_local = ens.download()
+    gathered = D.gather_members(u_local, args.members) if args.workload == "ensemble" else u_local
+    t_gather = D.max_over_ranks(time.perf_counter() - t0)
+    final_gather = {"ms": t_gather * 1e3, "bytes": int(8 * total_units * model._nvar),
+                    "what": "device -> host download on every rank + gather to rank 0",
+                    "value_incl_gather": total_units * args.steps / (t_max + t_gather)}
+    if rank == 0 and args.workload == "ensemble":
+        assert gathered.shape[0] == args.members
+    del gathered
 
     # -- end to end through the public API with HOST buffers: every step uploads the
     #    unknowns from pinned memory, steps, and downloads the result (the reference's
@@ -255,11 +313,19 @@ def run_gpu(args):
     for _ in range(e2e_steps):
         pipe.step_host(h_in, h_out, dt)
         h_in, h_out = h_out, h_in
-    t_e2e = D.max_over_ranks(time.perf_counter() - t0)
+    t_rank = time.perf_counter() - t0
+    t_e2e = D.max_over_ranks(t_rank)
+    link = 8.0 * N * nv * batch * e2e_steps / t_rank / 1e9     # GB/s each way on this rank
     e2e = {"value": total_units * e2e_steps / t_e2e, "unit": "grid-point*steps/s",
            "h2d_bytes_per_step": int(8 * N * nv * batch), "d2h_bytes_per_step": int(8 * N * nv * batch),
            "steps": e2e_steps, "ms_per_step": t_e2e * 1e3 / e2e_steps,
-           "api": "HostPipeline.step_host (%d member blocks on their own streams)" % len(pipe.parts)}
+           "api": "HostPipeline.step_host (%d member blocks on their own streams)" % len(pipe.parts),
+           "bytes_are": "per rank",
+           "link_gbs_each_way": {"rank0": round(link, 2),
+                                 "min_over_ranks": round(-D.max_over_ranks(-link), 2),
+                                 "sum_over_ranks": round(D.sum_over_ranks(link), 2)},
+           "host": affinity,
+           "limiter": "PCIe / host memory: upload and download of every step run concurrently"}
     assert not np.array_equal(u_before, h_in[0]), "the end-to-end pass did not advance the state"
     pipe.close()
     status = ens.state.status()
@@ -293,22 +359,22 @@ def run_gpu(args):
                 extras[other] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     cpu = None
     if rank == 0 and ws == 1 and not args.no_cpu:
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))   # the CPU arm uses every core
+        except OSError:
+            pass
         cpu = cpu_baseline(args.workload, args.cpu_seconds)
     if rank == 0:
         out = {
             "metric": "implicit grid-point*steps/s", "value": value,
             "unit": "grid-point*steps/s", "n_gpus": ws, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_max * 1e3 / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: %s" % (wk["cfg"], args.workload),
-                       "pde": mname, "scheme": wk["scheme"], "nodes": N,
-                       "systems_per_gpu": batch, "dt": dt, "fixed_step": True,
-                       "parallelism": "members sharded x%d, no collective" % ws,
-                       "l2": "working set %.0f MB per GPU > 126 MB L2" % (
-                           units * wk["Q"] / 1e6) if units * wk["Q"] > 126e6 else
-                       "working set %.0f MB fits L2; no flush (steps are dependent)" % (
-                           units * wk["Q"] / 1e6)},
+            "higher_is_better": True,
+            "scaling": "strong" if args.workload == "ensemble" else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": make_config(args, wk, mname, N,
+                                  args.members if args.workload == "ensemble" else ws, dt, ws),
+            "final_gather": final_gather,
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "other_workloads": extras,
         }
@@ -344,49 +410,72 @@ def quick_measure(workload, steps):
 
 
 # -------------------------------------------------------------- CPU baseline
-def _cpu_member(job):
-    name, r, N, steps = job
+def _cpu_kit():
+    """The reference's own CPU path -- its unmodified core files from baseline/_ref (copied by
+    build(); kind "reference") -- or, if they are not there, the oracle port (kind "port").
+    Returns (Model class, compiler argument, schemes module, kind)."""
+    try:
+        from oracle import ref_loader
+        if ref_loader.reference_root() is not None:
+            mods = ref_loader.load_reference()
+            return mods["model"].Model, "numpy", mods["schemes"], "reference"
+    except Exception:  # noqa: BLE001
+        pass
     from oracle import schemes as O
     from oracle.numpy_compiler import numpy_compiler
     from triflow_b200.model import Model
+    return Model, numpy_compiler, O, "port"
+
+
+_CPU = {}
+
+
+def _cpu_init():
+    """Per worker process, outside the timed region: build the model once (SymPy front-end +
+    lambdify take seconds; pickling a reference model drops its compiler, model.py:579-583)."""
+    Model, comp, schemes, kind = _cpu_kit()
+    _CPU.update(model=Model(**W.model_args("advdiff"), compiler=comp), schemes=schemes, kind=kind)
+
+
+def _cpu_member(job):
+    r, N, steps = job
+    m, schemes = _CPU["model"], _CPU["schemes"]
     c = W.ensemble(N, [r])
-    m = Model(**W.model_args("advdiff"), compiler=numpy_compiler)
     pars = dict(k=float(c["pars"]["k"][0]), c=float(c["pars"]["c"][0]), periodic=False)
     f = m.fields_template(x=c["x"], **c["fields"])
-    sch = O.ROS3PRw(m, time_stepping=False)
-    t0 = time.perf_counter()
+    sch = schemes.ROS3PRw(m, time_stepping=False)
     t = 0.0
     for _ in range(steps):
         t, f = sch(t, f, c["dt"], pars, hook=W.readme_hook)
-    return time.perf_counter() - t0
+    return _CPU["kind"]
 
 
 def cpu_rate(workload, budget_s, cores):
-    """Oracle port (numpy + SciPy SuperLU) of the same workload on host cores."""
-    from oracle import schemes as O
-    from oracle.numpy_compiler import numpy_compiler
-    from triflow_b200.model import Model
+    """The reference CPU path (numpy compiler + SciPy SuperLU) on the same workload, on host
+    cores.  Only stepping is timed: model construction and process start-up are outside."""
     if workload == "ensemble":
         import multiprocessing as mp
         N, steps = 4096, 20
-        t0 = time.perf_counter()
-        _cpu_member(("advdiff", 0, N, 2))
-        per = (time.perf_counter() - t0) / 2
-        nmem = max(cores, int(budget_s / max(per * steps, 1e-3)) * cores)
-        nmem = min(nmem, 512 * cores)
-        jobs = [("advdiff", int(r), N, steps)
-                for r in np.linspace(0, W.ENSEMBLE_K * W.ENSEMBLE_C - 1, nmem)]
-        t0 = time.perf_counter()
-        with mp.get_context("fork").Pool(cores) as pool:
-            pool.map(_cpu_member, jobs)
-        wall = time.perf_counter() - t0
-        return (N * nmem * steps / wall,
-                "%d of 32768 members x %d steps over %d processes" % (nmem, steps, cores))
-    mk = {"ks": (W.kuramoto, "ks", lambda m: O.ROS3PRw(m, time_stepping=False)),
-          "burgers": (lambda N=None: W.burgers(N or 2 ** 17, 1), "burgers_up1", O.ROS2),
-          "film": (W.film, "film", lambda m: O.Theta(m, theta=1))}[workload]
+        with mp.get_context("fork").Pool(cores, initializer=_cpu_init) as pool:
+            pool.map(_cpu_member, [(0, N, 1)] * cores)               # workers up, models built
+            t0 = time.perf_counter()
+            kind = pool.map(_cpu_member, [(0, N, 2)] * cores)[0]
+            per = (time.perf_counter() - t0) / 2
+            nmem = max(cores, int(budget_s / max(per * steps, 1e-3)) * cores)
+            nmem = min(nmem, 512 * cores)
+            jobs = [(int(r), N, steps)
+                    for r in np.linspace(0, W.ENSEMBLE_K * W.ENSEMBLE_C - 1, nmem)]
+            t0 = time.perf_counter()
+            pool.map(_cpu_member, jobs, chunksize=max(1, nmem // (4 * cores)))
+            wall = time.perf_counter() - t0
+        return (N * nmem * steps / wall, kind,
+                "%d of 32768 members x %d steps over %d processes (stepping only)" % (nmem, steps, cores))
+    Model, comp, schemes, kind = _cpu_kit()
+    mk = {"ks": (W.kuramoto, "ks", lambda m: schemes.ROS3PRw(m, time_stepping=False)),
+          "burgers": (lambda N=None: W.burgers(N or 2 ** 17, 1), "burgers_up1", schemes.ROS2),
+          "film": (W.film, "film", lambda m: schemes.Theta(m, theta=1))}[workload]
     c = mk[0]()
-    m = Model(**W.model_args(mk[1]), compiler=numpy_compiler)
+    m = Model(**W.model_args(mk[1]), compiler=comp)
     f = m.fields_template(x=c["x"], **c["fields"])
     sch = mk[2](m)
     t, n, t0 = 0.0, 0, time.perf_counter()
@@ -396,14 +485,14 @@ def cpu_rate(workload, budget_s, cores):
         if time.perf_counter() - t0 > budget_s or n >= 20:
             break
     wall = time.perf_counter() - t0
-    return (c["x"].size * n / wall, "%d steps at full size N=%d, 1 process "
+    return (c["x"].size * n / wall, kind, "%d steps at full size N=%d, 1 process "
             "(the path is single-threaded)" % (n, c["x"].size))
 
 
 def cpu_baseline(workload, budget_s):
     cores = (os.cpu_count() or 1) if workload == "ensemble" else 1
-    v, sample = cpu_rate(workload, budget_s, cores)
-    return {"value": v, "unit": "grid-point*steps/s", "cores": cores, "kind": "port",
+    v, kind, sample = cpu_rate(workload, budget_s, cores)
+    return {"value": v, "unit": "grid-point*steps/s", "cores": cores, "kind": kind,
             "sample": sample + "; rate extrapolated linearly"}
 
 
@@ -411,24 +500,30 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
     wk = WORKLOADS[args.workload]
+    dims = {"ensemble": ("advdiff", args.nodes or 4096, args.members, 0.025),
+            "ks": ("ks", args.nodes or 2 ** 20, ws, 0.2),
+            "burgers": ("burgers_up1", args.nodes or 2 ** 17, ws, 0.1),
+            "film": ("film", args.nodes or 2 ** 18, ws, 0.05)}[args.workload]
     cores = (os.cpu_count() or 1) if args.workload == "ensemble" else 1
     budget = max(2.0, min(25.0, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(min(args.warmup, 1)):
         cpu_rate(args.workload, 1.0, cores)
-    vals, sample = [], ""
+    vals, sample, kind = [], "", "port"
     for _ in range(max(1, min(args.steps, 3))):
-        v, sample = cpu_rate(args.workload, budget, cores)
+        v, kind, sample = cpu_rate(args.workload, budget, cores)
         vals.append(v)
     v = float(np.mean(vals))
     _emit({
         "impl": "reference", "metric": "implicit grid-point*steps/s", "value": v,
-        "unit": "grid-point*steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "unit": "grid-point*steps/s", "n_gpus": ws,
         "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (wk["cfg"], args.workload), "scheme": wk["scheme"]},
+        "scaling": "strong" if args.workload == "ensemble" else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": make_config(args, wk, dims[0], dims[1], dims[2], dims[3], ws),
         "cpu_baseline": {"value": v, "unit": "grid-point*steps/s", "cores": cores,
-                         "kind": "port", "sample": sample},
+                         "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "grid-point*steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0}})
 
@@ -444,7 +539,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ensemble", choices=sorted(WORKLOADS))
     ap.add_argument("--members", type=int, default=W.ENSEMBLE_K * W.ENSEMBLE_C,
-                    help="ensemble members per GPU")
+                    help="ensemble members IN TOTAL (sharded over the ranks)")
     ap.add_argument("--nodes", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-groups", type=int, default=16,

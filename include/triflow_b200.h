@@ -64,6 +64,9 @@ int tf_ctx_set_async(tf_ctx_t ctx, int enable);
 
 /* pinned host memory for upload / download buffers */
 int tf_host_alloc(size_t nbytes, void** out);
+/* write-combined variant for buffers the host only WRITES (upload sources): the device reads
+ * them over PCIe without snooping the CPU caches; reading them from the CPU is very slow */
+int tf_host_alloc_wc(size_t nbytes, void** out);
 int tf_host_free(void* p);
 
 /* Replaces numpy_compiler(model) -> (compute_F, compute_J)
@@ -166,6 +169,9 @@ long long tf_ctx_launch_count(tf_ctx_t ctx);
 /* CUDA-event timing on the context's stream: start/stop bracket, elapsed ms */
 int tf_ctx_timer_start(tf_ctx_t ctx);
 int tf_ctx_timer_stop(tf_ctx_t ctx, float* ms);
+/* measured fp64 throughput of the device (DFMA per second, 8 independent chains per thread):
+ * the denominator for kernels that are bound by the fp64 pipe rather than by HBM */
+int tf_ctx_fp64_peak(tf_ctx_t ctx, double* dfma_per_s);
 /* per-kernel-family accumulated device time (ms) since the last reset; names out */
 int tf_ctx_profile(tf_ctx_t ctx, int enable);
 int tf_ctx_profile_read(tf_ctx_t ctx, int family, float* ms, long long* launches);

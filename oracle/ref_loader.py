@@ -1,6 +1,8 @@
 """Loads the REFERENCE's own ``triflow/core/*.py`` -- unmodified, by file path -- for tests
 that drive the reference's objects (``Model``, ``Simulation``, ``F_Routine``) with this
-repository's CUDA compiler plugin and schemes.  Test infrastructure only.
+repository's CUDA compiler plugin and schemes, and for the reference arm of ``bench.py``
+(``--impl reference`` / ``cpu_baseline``), which times the reference's own CPU path.
+Test / measurement infrastructure only: nothing under ``triflow_b200/`` imports it.
 
 Source of the files: ``baseline/_ref/triflow/core`` (git-ignored copy made by
 ``__graft_entry__.build()`` from ``/root/reference``; it travels to the GPU box) or

@@ -109,6 +109,8 @@ def lib():
         "tf_ctx_create": [i, C.POINTER(vp)], "tf_ctx_destroy": [vp], "tf_ctx_sync": [vp],
         "tf_ctx_set_async": [vp, i],
         "tf_host_alloc": [C.c_size_t, C.POINTER(vp)], "tf_host_free": [vp],
+        "tf_host_alloc_wc": [C.c_size_t, C.POINTER(vp)],
+        "tf_ctx_fp64_peak": [vp, dp],
         "tf_model_load": [vp, vp, C.c_size_t, C.POINTER(ModelDesc), C.POINTER(vp)],
         "tf_model_unload": [vp],
         "tf_model_read_symbol": [vp, C.c_char_p, vp, C.c_size_t],
@@ -138,7 +140,7 @@ def lib():
 
 
 EXPORTS = ["tf_last_error", "tf_ctx_create", "tf_ctx_destroy", "tf_ctx_sync", "tf_ctx_set_async",
-           "tf_host_alloc",
+           "tf_host_alloc", "tf_host_alloc_wc", "tf_ctx_fp64_peak",
            "tf_host_free", "tf_model_load", "tf_model_unload", "tf_model_read_symbol", "tf_state_create",
            "tf_state_destroy", "tf_state_upload", "tf_state_download", "tf_eval_F",
            "tf_eval_J", "tf_scheme_create", "tf_scheme_destroy", "tf_hook_set_dirichlet",
@@ -195,11 +197,12 @@ def new_context(device=None):
 _pinned = []
 
 
-def pinned_empty(shape, dtype=np.float64):
-    """numpy array over page-locked host memory (for upload / download buffers)."""
+def pinned_empty(shape, dtype=np.float64, write_combined=False):
+    """numpy array over page-locked host memory (for upload / download buffers).
+    ``write_combined``: for buffers the host only writes (upload sources)."""
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     p = C.c_void_p()
-    check(lib().tf_host_alloc(n, C.byref(p)))
+    check((lib().tf_host_alloc_wc if write_combined else lib().tf_host_alloc)(n, C.byref(p)))
     buf = (C.c_char * max(n, 1)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     _pinned.append((p, buf))  # kept for the life of the process
