@@ -47,7 +47,7 @@ def kernel_bytes(wk, family, stage=None):
     §8d step model split over the launches (DESIGN.md 'Roofline accounting')."""
     v, w, s = wk["v"], wk["w"], wk["s"]
     B = v * v * w
-    if family == "sysstep":                      # whole step in one launch (system-resident path)
+    if family in ("sysstep", "gridstep"):        # whole step in one launch
         return wk["Q"]
     if family == "factor":
         return 8 * (B + v)                       # write factor, read U
@@ -261,6 +261,7 @@ def run_gpu(args):
                 "traffic": traffic,
                 "traffic_source": ("static ncu capture: " + sk["source"]) if traffic else None,
                 "peak_source": peak_src,
+                "limiter": sk.get("limiter"),
                 "kernel_share_of_step": round(dom_ms / tot_ms, 3),
                 "step_achieved": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4),
                 "bytes_per_node_step": wk["Q"],
@@ -283,9 +284,10 @@ def run_gpu(args):
                             "`traffic`, and what bounds it is the fp64 pipe / issue rate (`fp64`)")
 
     # -- final gather of the states to rank 0 (the only inter-GPU traffic of an ensemble)
+    h_final = _lib.pinned_empty((batch, N * model._nvar))
     D.barrier()
     t0 = time.perf_counter()
-    u_local = ens.download()
+    u_local = ens.download(out=h_final)
     gathered = D.gather_members(u_local, args.members) if args.workload == "ensemble" else u_local
     t_gather = D.max_over_ranks(time.perf_counter() - t0)
     final_gather = {"ms": t_gather * 1e3, "bytes": int(8 * total_units * model._nvar),

@@ -140,6 +140,23 @@ int tf_ensemble_advance(tf_state_t st, tf_scheme_t sc, double t, double dt, doub
                         double safety_factor, int max_iter, double dt_min, double* internal_dt,
                         int* n_fixed_steps, int* fail);
 
+/* Replaces schemes.time_stepping (core/schemes.py:33-66), the Richardson controller that
+ * Simulation wraps around EVERY scheme by default (core/simulation.py:190-197), for every
+ * member of an ensemble, on the device: one coarse scheme call over m*dt_ against ten fine
+ * calls over dt_, err = max_var ||coarse - fine||_2 / (m^2 - 1), dt_ <- sqrt(dt^2 tol / err),
+ * rejected (and repeated from the state reached, as the reference does) while
+ * dt_ < dt / reject_factor.  inner_adaptive != 0: the wrapped scheme runs its own
+ * embedded-error controller in every call (the reference's default double wrapping of
+ * ROS3PRw / ROS3PRL / RODASPR; in_* are that controller's arguments, inner_dt its per-member
+ * state); 0: every call is one fixed step (ROS2, Theta, time_stepping=False).
+ *   outer_dt  in/out per member, <= 0 means "None";  n_calls: scheme calls, n_fixed_steps:
+ *   fixed steps, fail: 0 or TF_E* per member (out, may be null). */
+int tf_ensemble_richardson(tf_state_t st, tf_scheme_t sc, int inner_adaptive, double t, double dt,
+                           double tol, int m, double reject_factor, double in_tol,
+                           double in_safety_factor, int in_max_iter, double in_dt_min,
+                           double* outer_dt, double* inner_dt, int* n_calls, int* n_fixed_steps,
+                           int* fail);
+
 /* Optional: keep the factorisation across steps while gamma*dt is unchanged.  Only valid
  * for models whose Jacobian does not depend on the state (linear models with uniform
  * parameters; the reference rebuilds and refactorises every step regardless,

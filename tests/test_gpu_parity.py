@@ -875,3 +875,55 @@ def test_pivot_growth_is_reported():
         with pytest.raises(RuntimeError, match="pivot growth"):
             ens.step(dt, 1)
         assert ens.state.status()[0] & 8
+
+
+# --------------------------- Simulation-default adaptivity for ensembles, on the device
+@pytest.mark.parametrize("sname", ["ROS3PRw", "ROS2", "Theta"])
+def test_ensemble_simulation_default_controllers(sname):
+    """Every member of an ensemble advanced the way an un-flagged reference ``Simulation``
+    advances one system: schemes.time_stepping (Richardson, core/schemes.py:33-66) around
+    the scheme, which for ROS3PRw(tol=...) runs its own embedded controller inside every call
+    (the double wrapping of core/simulation.py:190-197).  Member 0 is the README system: the
+    reference's own trajectory (golden); all members against the oracle, with identical
+    numbers of scheme calls and fixed steps."""
+    from oracle import schemes as O
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.ensemble import Ensemble
+    c = W.readme(200)
+    ks = np.array([.001, .002, .0005, .004])
+    cs = np.array([.03, -.05, .06, .01])
+    gm, om = gmodel("advdiff"), omodel("advdiff")
+    kw = dict(tol=1e-1) if sname == "ROS3PRw" else {}
+    ens = Ensemble(gm, getattr(S, sname)(gm, **kw), c["x"], c["fields"],
+                   dict(k=ks, c=cs, periodic=False), hook=S.Dirichlet(U=(1, 0)), batch=len(ks))
+    snaps, calls, fixed = [], [], []
+    for _ in range(5):
+        nc, nf = ens.advance_simulation_default(c["dt"])
+        snaps.append(ens.download().copy())
+        calls.append(nc.copy())
+        fixed.append(nf.copy())
+    snaps = np.array(snaps)                                    # (5, members, N)
+    if sname == "ROS3PRw":
+        g = traj()
+        assert rel_traj_err(snaps[:, 0], g["readme_simdefault_ROS3PRw"]) <= TRAJ_TOL
+    for r in range(len(ks)):
+        pars = dict(k=float(ks[r]), c=float(cs[r]), periodic=False)
+        inner = getattr(O, sname)(om, **kw)
+        count = {"calls": 0}
+        orig = inner.__call__
+
+        def counted(t, fields, dt, pars, hook=O.null_hook, _o=inner):
+            count["calls"] += 1
+            return type(_o).__call__(_o, t, fields, dt, pars, hook)
+        adaptive = O.time_stepping(counted)
+        f = om.fields_template(x=c["x"], **c["fields"])
+        t, ref, ref_calls = 0.0, [], []
+        for _ in range(5):
+            f, _p = W.readme_hook(t, f, pars)
+            n0 = count["calls"]
+            t, f = adaptive(t, f, c["dt"], pars, W.readme_hook)
+            ref.append(f.uflat.copy())
+            ref_calls.append(count["calls"] - n0)
+        assert rel_traj_err(snaps[:, r], np.array(ref)) <= TRAJ_TOL
+        assert [int(x[r]) for x in calls] == ref_calls
+        del orig

@@ -1779,22 +1779,26 @@ struct TfCtl {            // one per system
 
 extern "C" __global__ void tf_k_ctl_init(int batch, TfCtl* c, double* dtsys, double* asys, int* act,
                                          const double* internal_dt, double t0, double dt_out,
-                                         double gamma) {
+                                         double gamma, const double* t0v, const double* dtv,
+                                         const int* maskv) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= batch) return;
+  // (t0v / dtv / maskv: per-member start time, span and participation, or null)
+  const double ts = t0v ? t0v[s] : t0, span = dtv ? dtv[s] : dt_out;
+  const int on = maskv ? maskv[s] : 1;
   double d = internal_dt[s] < 0.0 ? 1e-6 : internal_dt[s];
-  d = d < dt_out ? d : dt_out;
-  c[s].t = t0;
-  c[s].next = t0 + dt_out;
-  c[s].dt_int = d;
+  d = d < span ? d : span;
+  c[s].t = ts;
+  c[s].next = ts + span;
+  c[s].dt_int = on ? d : internal_dt[s];
   c[s].dt_try = d;
-  c[s].phase = 0;
+  c[s].phase = on ? 0 : 2;
   c[s].iters = 0;
   c[s].nfs = 0;
   c[s].fail = 0;
   dtsys[s] = d;
   asys[s] = gamma * d;
-  act[s] = 1;
+  act[s] = on;
 }
 
 // after one attempt of every active member: accept / reject, next dt, commit flags
@@ -1851,6 +1855,147 @@ extern "C" __global__ void tf_k_commit(Geom g, double* __restrict__ U, const dou
   for (long long a = blockIdx.y * (long long)blockDim.x + threadIdx.x; a < vs;
        a += (long long)gridDim.y * blockDim.x)
     U[sys * vs + a] = Un[sys * vs + a];
+}
+
+// ---- outer Richardson controller of an ensemble: schemes.time_stepping (reference
+// core/schemes.py:33-66, the wrapper Simulation puts around EVERY scheme,
+// simulation.py:190-197), run independently for every member.  One attempt = one coarse
+// scheme call over m*dt_ against ten fine calls over dt_; the host only sequences the calls.
+struct TfRich {           // one per system
+  double t, target, idt, base, trial;
+  int phase;              // 0: attempting, 1: last call up to the target, 2: done
+  int calls, nfs, fail;
+};
+__device__ __forceinline__ void rich_decide(TfRich& r, int m) {
+  if (r.t + r.idt <= r.target) {            // while t + internal_dt <= next_step: one_step(internal_dt / m)
+    r.phase = 0;
+    r.base = r.idt / m;
+    r.trial = r.base;
+  } else if (r.t < r.target) {
+    r.phase = 1;
+  } else {
+    r.phase = 2;
+  }
+}
+extern "C" __global__ void tf_k_rich_init(int batch, TfRich* R, const double* idt_in, double t0,
+                                          double dt_out, int m) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= batch) return;
+  TfRich r;
+  r.t = t0;
+  r.target = t0 + dt_out;
+  r.idt = (idt_in[s] > 0.0) ? idt_in[s] : dt_out;      // "internal_dt if internal_dt else dt"
+  r.base = r.trial = 0.0;
+  r.calls = r.nfs = r.fail = 0;
+  rich_decide(r, m);
+  R[s] = r;
+}
+// arguments of the next scheme call of every member; which: 0 coarse (or the last call), 1 fine
+extern "C" __global__ void tf_k_rich_call(int batch, const TfRich* R, int which, double* dtcall,
+                                          double* acall, double* tcall, int* mask, int* n_on,
+                                          int m, double gamma) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= batch) return;
+  const TfRich r = R[s];
+  int on = 0;
+  double d = 0.0;
+  if (which == 0) {
+    if (r.phase == 0) { on = 1; d = m * r.trial; }
+    else if (r.phase == 1) { on = 1; d = r.target - r.t; }
+  } else if (r.phase == 0) {
+    on = 1;
+    d = r.trial;
+  }
+  dtcall[s] = d;
+  acall[s] = gamma * d;
+  tcall[s] = r.t;
+  mask[s] = on;
+  if (on) atomicAdd(n_on, 1);
+}
+// dst <- src for the members in the given phase
+extern "C" __global__ void tf_k_rich_copy(Geom g, const TfRich* R, int phase, double* __restrict__ dst,
+                                          const double* __restrict__ src) {
+  const int sys = blockIdx.x;
+  if (R[sys].phase != phase) return;
+  const long long vs = vstride(g);
+  for (long long a = blockIdx.y * (long long)blockDim.x + threadIdx.x; a < vs;
+       a += (long long)gridDim.y * blockDim.x)
+    dst[sys * vs + a] = src[sys * vs + a];
+}
+// bookkeeping after a scheme call (the call returns t + dt)
+extern "C" __global__ void tf_k_rich_after(int batch, TfRich* R, int which, const int* mask,
+                                           const TfCtl* c) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= batch || !mask[s]) return;
+  TfRich r = R[s];
+  r.calls += 1;
+  if (c != nullptr) {                       // inner scheme with its own controller
+    r.nfs += c[s].nfs;
+    if (c[s].fail && !r.fail) r.fail = c[s].fail;
+  } else {
+    r.nfs += 1;
+  }
+  if (which == 1) r.t = r.t + r.trial;
+  else if (r.phase == 1) { r.t = r.target; r.phase = 2; }
+  R[s] = r;
+}
+// err = max over variables of ||coarse - fine||_2 / (m^2 - 1); then the step-size decision
+extern "C" __global__ void __launch_bounds__(256) tf_k_rich_update(Geom g, TfRich* R, const double* __restrict__ U,
+                                                                   const double* __restrict__ Uc, double tol,
+                                                                   int m, double reject) {
+  const int sys = blockIdx.x;
+  __shared__ double s_red[8][V];
+  __shared__ TfRich s_r;
+  if (threadIdx.x == 0) s_r = R[sys];
+  __syncthreads();
+  if (s_r.phase != 0) return;
+  const long long vs = vstride(g);
+  double acc[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) acc[e] = 0.0;
+  for (int i = threadIdx.x; i < g.N; i += blockDim.x) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const double d = Uc[sys * vs + vidx(i, e)] - U[sys * vs + vidx(i, e)];
+      acc[e] = __fma_rn(d, d, acc[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], d);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][e] = acc[e];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double err = 0.0;
+    for (int e = 0; e < V; ++e) {
+      double v = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += s_red[w][e];
+      const double en = sqrt(v) / (double)(m * m - 1);
+      err = (en > err || en != en) ? en : err;
+    }
+    TfRich r = s_r;
+    const double nd = sqrt(r.base * r.base * tol / err);
+    if (nd < r.base / reject) {
+      r.trial = nd;                          // rejected: again, from the state reached
+    } else {
+      r.idt = nd;
+      rich_decide(r, m);
+    }
+    if (r.fail) r.phase = 2;
+    R[sys] = r;
+  }
+}
+extern "C" __global__ void tf_k_rich_read(int batch, const TfRich* R, double* idt, int* calls, int* nfs,
+                                          int* fail, int* n_on) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= batch) return;
+  idt[s] = R[s].idt;
+  calls[s] = R[s].calls;
+  nfs[s] = R[s].nfs;
+  fail[s] = R[s].fail;
+  if (R[s].phase != 2) atomicAdd(n_on, 1);
 }
 
 extern "C" __global__ void tf_k_ctl_read(int batch, const TfCtl* c, double* internal_dt, int* nfs,

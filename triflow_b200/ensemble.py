@@ -104,6 +104,37 @@ class Ensemble:
         self.t += dt
         return self.n_fixed_steps
 
+    def advance_simulation_default(self, dt, tol=1e-1, m=10, reject_factor=2):
+        """Advance every member to ``t + dt`` the way an un-flagged ``Simulation(...)`` of
+        the reference does: its Richardson controller ``schemes.time_stepping``
+        (``core/schemes.py:33-66``, applied by ``core/simulation.py:190-197`` to every scheme)
+        around the scheme -- which, for the Rosenbrock schemes constructed with a tolerance
+        (``time_stepping=True``), runs its own embedded-error controller inside every call.
+        Each member has its own controllers; everything runs on the device.
+        Returns ``(scheme calls, fixed steps)`` per member."""
+        import ctypes as C
+        sch = self.scheme
+        inner = bool(getattr(sch, "_time_control", False))
+        if inner and (getattr(sch, "_b_pred", None) is None or sch._tol is None):
+            raise ValueError("the wrapped scheme's own controller needs b_pred and a tolerance")
+        if not hasattr(self, "_outer_dt"):
+            self._outer_dt = np.zeros(self.batch)            # None
+        if not hasattr(self, "_internal_dt"):
+            self._internal_dt = np.full(self.batch, -1.0)
+        calls, nfs, fail = ((C.c_int * self.batch)() for _ in range(3))
+        rc = _lib.lib().tf_ensemble_richardson(
+            self.state.h, sch.handle, int(inner), float(self.t), float(dt), float(tol), int(m),
+            float(reject_factor), float(sch._tol or 0.0) if inner else 0.0,
+            float(getattr(sch, "_safety_factor", 0.9)), int(getattr(sch, "_max_iter", 0) or 0),
+            float(getattr(sch, "_dt_min", 0.0) or 0.0), _lib.dptr(self._outer_dt),
+            _lib.dptr(self._internal_dt), calls, nfs, fail)
+        self.n_scheme_calls = np.array(calls[:])
+        self.n_fixed_steps = np.array(nfs[:])
+        self.failed = np.array(fail[:])
+        _lib.check(rc)
+        self.t += dt
+        return self.n_scheme_calls, self.n_fixed_steps
+
     def download(self, out=None):
         return self.state.download(out)
 
