@@ -31,6 +31,7 @@ typedef struct tf_ctx_s* tf_ctx_t;
 typedef struct tf_model_s* tf_model_t;
 typedef struct tf_state_s* tf_state_t;
 typedef struct tf_scheme_s* tf_scheme_t;
+typedef struct tf_ring_s* tf_ring_t;
 
 /* Static description of a lowered model (produced by triflow_b200/codegen.py from
  * the attributes a compiler plugin receives: core/model.py:244-291). */
@@ -186,6 +187,20 @@ long long tf_ctx_launch_count(tf_ctx_t ctx);
 /* CUDA-event timing on the context's stream: start/stop bracket, elapsed ms */
 int tf_ctx_timer_start(tf_ctx_t ctx);
 int tf_ctx_timer_stop(tf_ctx_t ctx, float* ms);
+/* Output ring: the device-resident output path behind Simulation.stream / the container's
+ * buffered writes (core/simulation.py:244-253, plugins/container.py:99-137).  tf_ring_push
+ * snapshots the current state (uflat layout, core/fields.py:146-159) into the next of `slots`
+ * pinned host buffers with an asynchronous copy on the ring's own stream and returns at once:
+ * stepping continues while the copy runs.  tf_ring_pop hands out the oldest snapshot (block:
+ * wait for its copy; else *data stays NULL if it is not there yet); tf_ring_release frees its
+ * slot.  push fails with TF_EINVAL when all slots are in flight.  One producer thread (the one
+ * stepping the state) and one consumer thread may use a ring concurrently. */
+int tf_ring_create(tf_state_t st, int slots, tf_ring_t* out);
+int tf_ring_destroy(tf_ring_t ring);
+int tf_ring_push(tf_ring_t ring, double t);
+int tf_ring_pop(tf_ring_t ring, int block, const double** data, double* t);
+int tf_ring_release(tf_ring_t ring);
+
 /* measured fp64 throughput of the device (DFMA per second, 8 independent chains per thread):
  * the denominator for kernels that are bound by the fp64 pipe rather than by HBM */
 int tf_ctx_fp64_peak(tf_ctx_t ctx, double* dfma_per_s);

@@ -111,6 +111,9 @@ def lib():
         "tf_host_alloc": [C.c_size_t, C.POINTER(vp)], "tf_host_free": [vp],
         "tf_host_alloc_wc": [C.c_size_t, C.POINTER(vp)],
         "tf_ctx_fp64_peak": [vp, dp],
+        "tf_ring_create": [vp, i, C.POINTER(vp)], "tf_ring_destroy": [vp],
+        "tf_ring_push": [vp, d], "tf_ring_pop": [vp, i, C.POINTER(dp), dp],
+        "tf_ring_release": [vp],
         "tf_model_load": [vp, vp, C.c_size_t, C.POINTER(ModelDesc), C.POINTER(vp)],
         "tf_model_unload": [vp],
         "tf_model_read_symbol": [vp, C.c_char_p, vp, C.c_size_t],
@@ -142,7 +145,8 @@ def lib():
 
 
 EXPORTS = ["tf_last_error", "tf_ctx_create", "tf_ctx_destroy", "tf_ctx_sync", "tf_ctx_set_async",
-           "tf_host_alloc", "tf_host_alloc_wc", "tf_ctx_fp64_peak",
+           "tf_host_alloc", "tf_host_alloc_wc", "tf_ctx_fp64_peak", "tf_ring_create",
+           "tf_ring_destroy", "tf_ring_push", "tf_ring_pop", "tf_ring_release",
            "tf_host_free", "tf_model_load", "tf_model_unload", "tf_model_read_symbol", "tf_state_create",
            "tf_state_destroy", "tf_state_upload", "tf_state_download", "tf_eval_F",
            "tf_eval_J", "tf_scheme_create", "tf_scheme_destroy", "tf_hook_set_dirichlet",

@@ -15,6 +15,8 @@ Layout contract (reference ``fields.py:146-159,173-183``)::
 ``fill`` is the exact inverse.
 """
 
+import ctypes
+
 import numpy as np
 
 
@@ -111,6 +113,22 @@ class BaseFields:
         return new
 
     __copy__ = copy
+
+    def with_uflat(self, uflat):
+        """New container that SHARES ``x`` and the helper fields with this one and whose
+        unknowns are strided views of one private copy of ``uflat`` (one pass over the data
+        instead of ``copy()`` + ``fill()``; used by the output ring's consumer)."""
+        src = np.ascontiguousarray(uflat, dtype=np.float64)
+        flat = np.empty(src.size, dtype=np.float64)
+        # (a foreign call: the GIL is released while the snapshot is copied, so the thread
+        #  that keeps stepping is not held up by the consumer)
+        ctypes.memmove(flat.ctypes.data, src.ctypes.data, src.nbytes)
+        flat = flat.reshape(self.size, -1)
+        new = object.__new__(type(self))
+        new._data = dict(self._data)
+        for e, var in enumerate(self.dependent_variables):
+            new._data[var] = flat[:, e].view(FieldArray)
+        return new
 
     def to_df(self):
         import pandas as pd
