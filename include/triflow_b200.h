@@ -201,6 +201,30 @@ int tf_ring_push(tf_ring_t ring, double t);
 int tf_ring_pop(tf_ring_t ring, int block, const double** data, double* t);
 int tf_ring_release(tf_ring_t ring);
 
+/* ---- One grid over several GPUs.  The reference has no analogue: it grows N only
+ * through sparse storage on one host (source_doc/source/user_guide.rst:183-187); the solve that
+ * is split here is `factorized(A)` / `luf(b)` of core/schemes.py:149,157 and the stencil
+ * evaluation of core/compilers.py:281-332 at the slab edges.
+ * Every rank (one GPU each) owns a slab of consecutive nodes, a whole number of tiles of the
+ * grid-resident step kernel; rank r of `nranks` creates its slab of the N-node grid with
+ * tf_state_create_slab, uploads / downloads ITS nodes only (tf_state_upload / _download with
+ * n_local values, node_off .. node_off + n_local - 1 of the grid), publishes its record area
+ * (tf_state_slab_export: a 64-byte CUDA IPC handle) and maps everybody else's
+ * (tf_state_slab_attach: handles of all ranks in rank order).  tf_scheme_step then runs the
+ * SAME step kernel on every GPU at once: halo values, scan records and the periodic border
+ * block cross the slab boundaries as tagged 16-byte words read straight from the peer GPU's
+ * memory over NVLink -- no collective call and no kernel boundary inside a step.  All ranks
+ * must call tf_scheme_step with the same arguments; the error estimate returned is the rank's
+ * own (reduce with max over ranks).  Scalar models with uniform parameters, tableaux of at
+ * most 3 stages, fixed steps, no hooks.  tf_state_slab_attach_local is the single-process
+ * form: the states of all ranks (rank order) live in the calling process. */
+int tf_state_create_slab(tf_ctx_t ctx, tf_model_t m, int N, int periodic, int rank, int nranks,
+                         tf_state_t* out);
+int tf_state_slab_info(tf_state_t st, int* node_off, int* n_local, int* tiles_local, int* tiles_total);
+int tf_state_slab_export(tf_state_t st, void* handle64);
+int tf_state_slab_attach(tf_state_t st, const void* handles);
+int tf_state_slab_attach_local(tf_state_t st, const tf_state_t* all);
+
 /* measured fp64 throughput of the device (DFMA per second, 8 independent chains per thread):
  * the denominator for kernels that are bound by the fp64 pipe rather than by HBM */
 int tf_ctx_fp64_peak(tf_ctx_t ctx, double* dfma_per_s);

@@ -127,6 +127,10 @@ def lib():
         "tf_scheme_advance": [vp, vp, d, d, d, d, i, d, i, dp, C.POINTER(i), dp],
         "tf_state_status": [vp, C.POINTER(i)], "tf_state_set_factor_reuse": [vp, i],
         "tf_state_set_fusion": [vp, i],
+        "tf_state_create_slab": [vp, vp, i, i, i, i, C.POINTER(vp)],
+        "tf_state_slab_info": [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)],
+        "tf_state_slab_export": [vp, vp], "tf_state_slab_attach": [vp, vp],
+        "tf_state_slab_attach_local": [vp, C.POINTER(vp)],
         "tf_ensemble_advance": [vp, vp, d, d, d, d, i, d, dp, C.POINTER(i), C.POINTER(i)],
         "tf_ensemble_richardson": [vp, vp, i, d, d, d, i, d, d, d, i, d, dp, dp, C.POINTER(i),
                                    C.POINTER(i), C.POINTER(i)],
@@ -152,6 +156,8 @@ EXPORTS = ["tf_last_error", "tf_ctx_create", "tf_ctx_destroy", "tf_ctx_sync", "t
            "tf_eval_J", "tf_scheme_create", "tf_scheme_destroy", "tf_hook_set_dirichlet",
            "tf_hook_clear", "tf_scheme_step", "tf_scheme_advance", "tf_state_status",
            "tf_state_set_factor_reuse", "tf_state_set_fusion", "tf_ensemble_advance",
+           "tf_state_create_slab", "tf_state_slab_info", "tf_state_slab_export",
+           "tf_state_slab_attach", "tf_state_slab_attach_local",
            "tf_ensemble_richardson",
            "tf_ctx_launch_count", "tf_ctx_timer_start", "tf_ctx_timer_stop",
            "tf_ctx_profile", "tf_ctx_profile_read"]

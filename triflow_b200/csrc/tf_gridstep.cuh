@@ -32,13 +32,33 @@
 // (compilers.py:292-332, schemes.py:146-149), the s stages of ROW_general._fixed_step
 // (schemes.py:150-163), update and error norm (:164-174); Theta (:548-559) is the 1-stage case.
 //
+// Several GPUs, one grid: the same kernel, one slab of whole tiles per GPU.  A tile's
+// records live in the record area of the GPU that owns the tile; the few tiles next to a slab
+// boundary (and the border-block protocol) read their neighbours' words straight out of the
+// peer GPU's memory over NVLink (IPC-mapped record areas, system-scope loads) -- the halo
+// exchange and the reduced-system coupling are fused into the step kernel, there is no
+// collective call and no kernel boundary between ranks.  The stage state at slab edges of the
+// NEXT step travels the same way (words tagged with the next epoch).
+//
 // Scope: scalar models (V == 1) without helper fields, s <= 3, one system (batch == 1),
-// tiles <= resident CTAs.  Everything else keeps the per-kernel pipeline.
-#pragma once
+// tiles <= resident CTAs (per GPU).  Everything else keeps the per-kernel pipeline.
+//
+// This file is included twice (tf_kernels.cuh): TF_GS_MULTI 0 -> tf_k_gridstep (one GPU: nothing
+// of the several-GPU form is compiled in, its branches cost the single-GPU kernel 17-25 %),
+// TF_GS_MULTI 1 -> tf_k_gridstep_mr + tf_k_gs_seed (slab states).
 
 #if (TF_NVAR == 1) && (TF_NHELP == 0)
 #define TF_HAS_GRIDSTEP 1
 
+#if TF_GS_MULTI
+#define GS_NS gs_multi
+#define TF_GS_KNAME tf_k_gridstep_mr
+#else
+#define GS_NS gs_single
+#define TF_GS_KNAME tf_k_gridstep
+#endif
+
+#ifndef TF_GS_ONCE
 #ifndef TF_GS_NT
 #define TF_GS_NT 448      /* max threads per CTA: 14 warps (4 per scheduler at most) x 128 registers */
 #endif
@@ -55,6 +75,14 @@ __device__ unsigned long long tf_gs_trace[256 * 32];
 #define GS_STAMP(ph) do { } while (0)
 #endif
 
+// where every tile of an aborted launch was waiting (wait site, 0: not waiting); read by
+// tools/slab_check.py through tf_model_read_symbol
+__device__ int tf_gs_stuck[1024];
+__device__ unsigned long long tf_gs_when[2];     // globaltimer: launch start (tile 0), first time-out
+__device__ __forceinline__ void gs_note_stuck(int ltile, int site) {
+  if (tf_gs_stuck[ltile & 1023] == 0) tf_gs_stuck[ltile & 1023] = site;
+}
+
 namespace tfk {
 
 #ifndef TF_GS_G
@@ -67,6 +95,16 @@ constexpr int GS_NPH = 1 + 2 * 3;               // look-back phases: factor, (fw
 constexpr int GS_STAGES = 3;
 static_assert(32 % GS_G == 0, "a thread's chunks lie in one warp-block");
 static_assert(C % BETA == 0, "streaming factorisation walks sub-blocks of BETA rows");
+// words per halo slot: the stage state of P nodes; at stage 0 the factorisation's windows reach
+// P + EX nodes into the next tile (rows of the next chunk), read as words across GPUs
+constexpr int GS_HW = P + EX;
+static_assert(GS_HW <= M, "the first chunk of a tile publishes its left halo");
+}  // namespace tfk
+#endif  // TF_GS_ONCE
+
+namespace tfk {
+namespace GS_NS {
+constexpr bool GS_MULTI = TF_GS_MULTI != 0;
 
 // ---- map of the first forward sweep of a periodic system.  The border fill (W = L^-1 E,
 //      G^T = F^T U^-1) consists of forward recurrences whose right-hand sides are non-zero in the
@@ -109,6 +147,7 @@ struct AffB {
     return o;
   }
 };
+using tfk::absorbing;            // (the overloads for the pipeline's maps)
 __device__ __forceinline__ bool absorbing(const AffB& m) {
   bool z = true;
 #pragma unroll
@@ -117,31 +156,57 @@ __device__ __forceinline__ bool absorbing(const AffB& m) {
 }
 constexpr int GS_KMAX = KMAX > AffB::K ? KMAX : AffB::K;
 
-// ---- record area (device memory, 16-byte words); offsets in words for `tiles` tiles
+// ---- several GPUs: kernel argument describing the slab decomposition (tf_params.h: TfGsMulti)
+// ---- record area (device memory, 16-byte words).  Every rank owns `tiles` (= tiles per rank)
+//      consecutive tiles and keeps THEIR records in its own area `bases[rank]`; accessors take
+//      the global tile index.  The single words live with the rank that writes them: w0 with
+//      rank 0 (first chunk), x_b and F_top with the last rank (border rows).
 struct GsRec {
-  LbWord* base;
-  int tiles;
+  LbWord* bases[TF_GS_MAXRANKS];
+  LbWord* base;          // own area
+  int tiles;             // tiles per rank
+  int nranks;
+  __device__ __forceinline__ LbWord* area(int& tile) const {     // owner's area; tile -> local index
+    if (!GS_MULTI || nranks == 1) return base;
+    const int r = tile / tiles;
+    tile -= r * tiles;
+    return bases[r];
+  }
   __device__ __forceinline__ LbWord* lb(int ph, int tile, int which) const {   // which: 0 agg, 1 inc
+    LbWord* base = area(tile);
     return base + (((long long)ph * tiles + tile) * 2 + which) * GS_KMAX;
   }
   __device__ __forceinline__ long long o_halo() const { return (long long)GS_NPH * tiles * 2 * GS_KMAX; }
   __device__ __forceinline__ LbWord* halo(int stage, int tile, int slot) const {
-    return base + o_halo() + (((long long)stage * tiles + tile) * 3 + slot) * P;
+    LbWord* base = area(tile);
+    return base + o_halo() + (((long long)stage * tiles + tile) * 3 + slot) * GS_HW;
   }
-  __device__ __forceinline__ long long o_lnext() const { return o_halo() + (long long)GS_STAGES * tiles * 3 * P; }
-  __device__ __forceinline__ LbWord* lnext(int tile) const { return base + o_lnext() + (long long)tile * BETA * BETA; }
+  __device__ __forceinline__ long long o_lnext() const { return o_halo() + (long long)GS_STAGES * tiles * 3 * GS_HW; }
+  __device__ __forceinline__ LbWord* lnext(int tile) const {
+    LbWord* base = area(tile);
+    return base + o_lnext() + (long long)tile * BETA * BETA;
+  }
   __device__ __forceinline__ long long o_alive() const { return o_lnext() + (long long)tiles * BETA * BETA; }
-  __device__ __forceinline__ LbWord* alive(int tile) const { return base + o_alive() + tile; }
+  __device__ __forceinline__ LbWord* alive(int tile) const {
+    LbWord* base = area(tile);
+    return base + o_alive() + tile;
+  }
   __device__ __forceinline__ long long o_gpart() const { return o_alive() + tiles; }
   __device__ __forceinline__ LbWord* gpart(int stage, int tile) const {
+    LbWord* base = area(tile);
     return base + o_gpart() + ((long long)stage * tiles + tile) * NB;
   }
   __device__ __forceinline__ long long o_spart() const { return o_gpart() + (long long)GS_STAGES * tiles * NB; }
-  __device__ __forceinline__ LbWord* spart(int tile) const { return base + o_spart() + (long long)tile * NB * NB; }
+  __device__ __forceinline__ LbWord* spart(int tile) const {
+    LbWord* base = area(tile);
+    return base + o_spart() + (long long)tile * NB * NB;
+  }
   __device__ __forceinline__ long long o_misc() const { return o_spart() + (long long)tiles * NB * NB; }
-  __device__ __forceinline__ LbWord* xb(int stage) const { return base + o_misc() + stage * NB; }
-  __device__ __forceinline__ LbWord* ftop() const { return base + o_misc() + GS_STAGES * NB; }
-  __device__ __forceinline__ LbWord* w0() const { return base + o_misc() + GS_STAGES * NB + NB * NB; }   // [2][NB][BETA]
+  __device__ __forceinline__ LbWord* last_area() const { return (!GS_MULTI || nranks == 1) ? base : bases[nranks - 1]; }
+  __device__ __forceinline__ LbWord* first_area() const { return (!GS_MULTI || nranks == 1) ? base : bases[0]; }
+  __device__ __forceinline__ LbWord* xb(int stage) const { return last_area() + o_misc() + stage * NB; }
+  __device__ __forceinline__ LbWord* ftop() const { return last_area() + o_misc() + GS_STAGES * NB; }
+  __device__ __forceinline__ LbWord* w0() const { return first_area() + o_misc() + GS_STAGES * NB + NB * NB; }   // [2][NB][BETA]
   __device__ __forceinline__ long long o_err() const { return o_misc() + GS_STAGES * NB + NB * NB + 2 * NB * BETA; }
   __device__ __forceinline__ double* errt() const { return (double*)(base + o_err()); }   // [tiles] doubles
 };
@@ -170,15 +235,42 @@ struct GsCtx {
   GsShared* sh;
   int* status;
   long long tag;
-  int tile, tiles, T;
+  int tile, tiles, T;     // GLOBAL tile index / tile count
+  int ltile;              // tile index on this rank
+  int rank, nranks;
+  int node_off;           // global index of this rank's first node (== first row: V == 1)
+  int nodes_local;        // node slots of this rank's slab (tiles per rank x tile nodes)
 };
+
+// Across GPUs the words are read over NVLink: system scope (peer data is not cached in L2,
+// and a gpu-scope load may be served from L1)
+__device__ __forceinline__ void ld_word_sys(const LbWord* p, double& v, long long& t) {
+  long long a;
+  asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(t) : "l"(p) : "memory");
+  v = __longlong_as_double(a);
+}
+__device__ __forceinline__ void st_word_sys(LbWord* p, double v, long long tag) {
+  long long o0, o1;
+  asm volatile(
+      "{\n.reg .b128 q, r;\nmov.b128 q, {%3, %4};\n"
+      "atom.relaxed.sys.global.exch.b128 r, [%2], q;\nmov.b128 {%0, %1}, r;\n}"
+      : "=l"(o0), "=l"(o1)
+      : "l"(p), "l"(__double_as_longlong(v)), "l"(tag)
+      : "memory");
+}
 
 // ---- bounded waits on tagged words
 // (the first tile that gives up records where: status = 4 | site << 8 | tile << 16)
 __device__ __forceinline__ bool gs_aborted(GsCtx& cx, int spins, int site) {
-  if (cx.sh->abort) return true;
-  if ((spins & 1023) == 1023 && (ld_flag(cx.status) & 4)) { cx.sh->abort = 1; return true; }
+  if (cx.sh->abort) { gs_note_stuck(cx.ltile, site); return true; }
+  if ((spins & 1023) == 1023 && (ld_flag(cx.status) & 4)) {
+    cx.sh->abort = 1;
+    gs_note_stuck(cx.ltile, site);
+    return true;
+  }
   if (spins > TF_GS_SPIN) {
+    gs_note_stuck(cx.ltile, site | 0x100);
+    if (!(ld_flag(cx.status) & 4)) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tf_gs_when[1]));
     const int code = 4 | (site << 8) | (cx.tile << 16);
     int old = ld_flag(cx.status);
     while (!(old & 4)) {
@@ -196,23 +288,64 @@ __device__ __noinline__ double gs_wait(GsCtx& cx, const LbWord* p, int site) {
   long long t;
   int spins = 0;
   while (true) {
-    ld_word(p, v, t);
+    if (GS_MULTI && cx.nranks > 1) ld_word_sys(p, v, t); else ld_word(p, v, t);
     if (t == cx.tag) return v;
     if (gs_aborted(cx, ++spins, site)) return 0.0;
   }
 }
-__device__ __forceinline__ void gs_post(GsCtx& cx, LbWord* p, double v) { st_word(p, v, cx.tag); }
+__device__ __forceinline__ void gs_post_tag(GsCtx& cx, LbWord* p, double v, long long tag) {
+  if (GS_MULTI && cx.nranks > 1) st_word_sys(p, v, tag); else st_word(p, v, tag);
+}
+__device__ __forceinline__ void gs_post(GsCtx& cx, LbWord* p, double v) { gs_post_tag(cx, p, v, cx.tag); }
+// (look-back records: same, whole maps)
+template <class Mon>
+__device__ __forceinline__ void gs_publish(GsCtx& cx, LbWord* dst, const Mon& m, long long tag, int lane) {
+  if (!GS_MULTI || cx.nranks == 1) { lb_publish(dst, m, tag, lane); return; }
+  if constexpr (GS_MULTI) {
+#pragma unroll
+    for (int k0 = 0; k0 < Mon::K; k0 += 32) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k0 + k < Mon::K && lane == k) v = m.d[(k0 + k < Mon::K) ? k0 + k : 0];
+      if (k0 + lane < Mon::K) st_word_sys(dst + k0 + lane, v, tag);
+    }
+  }
+}
+template <class Mon>
+__device__ __forceinline__ void gs_read2(GsCtx& cx, const LbWord* pi, const LbWord* pa, Mon& mi, Mon& ma,
+                                         long long FI, long long FA, bool& isI, bool& isA) {
+  if (!GS_MULTI || cx.nranks == 1) { lb_read2(pi, pa, mi, ma, FI, FA, isI, isA); return; }
+  if constexpr (GS_MULTI) {
+    long long ti[Mon::K], ta[Mon::K];
+#pragma unroll
+    for (int k = 0; k < Mon::K; ++k) ld_word_sys(pi + k, mi.d[k], ti[k]);
+#pragma unroll
+    for (int k = 0; k < Mon::K; ++k) ld_word_sys(pa + k, ma.d[k], ta[k]);
+    isI = true;
+    isA = true;
+#pragma unroll
+    for (int k = 0; k < Mon::K; ++k) {
+      isI = isI && (ti[k] == FI);
+      isA = isA && (ta[k] == FA);
+    }
+  }
+}
 
 // ---- decoupled look-back (see lookback() in tf_kernels.cuh; bounded, own record arrays)
+// (lt: position of the tile in the order of the scan; records are stored under the REAL tile
+//  index, i.e. in the area of the GPU that owns and writes them)
 template <class Mon>
-__device__ __noinline__ Mon gs_lookback(const Mon& aggregate, GsCtx& cx, int ph, int lt, int lane) {
+__device__ __noinline__ Mon gs_lookback(const Mon& aggregate, GsCtx& cx, int ph, int lt, int lane,
+                                        bool rev) {
   const long long FA = cx.tag * 4 + 1, FI = cx.tag * 4 + 2;
+  auto real = [&](int l) { return rev ? cx.tiles - 1 - l : l; };
   // logical tile lt of phase ph lives in slot lt (the backward phases number tiles from the end)
   if (lt == 0) {
-    lb_publish(cx.rec.lb(ph, 0, 1), aggregate, FI, lane);
+    gs_publish(cx, cx.rec.lb(ph, real(0), 1), aggregate, FI, lane);
     return Mon::identity();
   }
-  lb_publish(cx.rec.lb(ph, lt, 0), aggregate, FA, lane);
+  gs_publish(cx, cx.rec.lb(ph, real(lt), 0), aggregate, FA, lane);
   Mon prefix = Mon::identity();
   int look = lt - 1;
   bool finished = false;
@@ -227,7 +360,7 @@ __device__ __noinline__ Mon gs_lookback(const Mon& aggregate, GsCtx& cx, int ph,
       if (t >= 0 && (first || (lane < need && !ready))) {
         Mon ea;
         bool isA;
-        lb_read2(cx.rec.lb(ph, t, 1), cx.rec.lb(ph, t, 0), e, ea, FI, FA, isI, isA);
+        gs_read2(cx, cx.rec.lb(ph, real(t), 1), cx.rec.lb(ph, real(t), 0), e, ea, FI, FA, isI, isA);
         if (!isI) e = ea;
         ready = isI || isA;
       }
@@ -258,7 +391,7 @@ __device__ __noinline__ Mon gs_lookback(const Mon& aggregate, GsCtx& cx, int ph,
     prefix = Mon::combine(w, prefix);
     look -= 32;
   }
-  lb_publish(cx.rec.lb(ph, lt, 1), Mon::combine(prefix, aggregate), FI, lane);
+  gs_publish(cx, cx.rec.lb(ph, real(lt), 1), Mon::combine(prefix, aggregate), FI, lane);
   return prefix;
 }
 
@@ -304,7 +437,7 @@ __device__ __forceinline__ Mon gs_scan(const Mon& mine, GsCtx& cx, int ph) {
   if (warp == 0) {
     const Mon total = shfl_idx(wi, nwarps - 1);
     const int lt = REV ? cx.tiles - 1 - cx.tile : cx.tile;
-    const Mon tp = gs_lookback(total, cx, ph, lt, lane);
+    const Mon tp = gs_lookback(total, cx, ph, lt, lane, REV);
     if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < Mon::K; ++k) smem[GS_MAXW * GS_KMAX + k] = tp.d[k];
@@ -320,8 +453,8 @@ __device__ __forceinline__ Mon gs_scan(const Mon& mine, GsCtx& cx, int ph) {
 // ---- geometry of a thread's chunks
 struct GsThread {
   int t, T;            // thread in tile, threads per tile
-  int chunk0;          // first chunk (global index)
-  int blk, cl;         // warp-block and lane of the first chunk in the lane-transposed layout
+  int chunk0;          // first chunk, GLOBAL index (all row / node logic)
+  int blk, cl;         // warp-block (on this rank) and lane of the first chunk in the layout
   bool active;
   __device__ __forceinline__ long long cb(int h) const { return ((long long)blk * C) * 32 + cl + h; }
 };
@@ -332,8 +465,8 @@ __device__ __forceinline__ int gs_ss(int r, int h, int t, int T) { return (r * G
 // stage state of node j (any tile) from global memory: U + ((alpha_0 k_0 + ...)).  Valid for
 // nodes of the own tile (same-CTA writes, ordered by a barrier) and, at stage 0, for any node.
 template <int I>
-__device__ __forceinline__ double gs_state_global(const Buf& b, int j, const TfStepDesc& sd) {
-  const long long a = vidx(j, 0);
+__device__ __forceinline__ double gs_state_global(const GsCtx& cx, const Buf& b, int j, const TfStepDesc& sd) {
+  const long long a = vidx(GS_MULTI ? j - cx.node_off : j, 0);
   double u = b.U[a];
   if (I > 0) {
     double acc = 0.0;
@@ -352,23 +485,48 @@ __device__ __noinline__ double gs_node_value(GsCtx& cx, const Geom& g, const Buf
                                              const TfStepDesc& sd) {
   const int TN = cx.T * GS_G * M;
   const int ot = jm / TN;
-  if (I == 0 || ot == cx.tile) return gs_state_global<I>(b, jm, sd);
+  const bool mine = !GS_MULTI || (jm >= cx.node_off && jm < cx.node_off + cx.nodes_local);
+  if (ot == cx.tile || (I == 0 && mine)) return gs_state_global<I>(cx, b, jm, sd);
   const int loc = jm - ot * TN;
-  if (loc < P) return gs_wait(cx, cx.rec.halo(I, ot, 0) + loc, 10);
+  if (loc < (I == 0 ? GS_HW : P)) return gs_wait(cx, cx.rec.halo(I, ot, 0) + loc, 10);
   if (loc >= TN - P) return gs_wait(cx, cx.rec.halo(I, ot, 1) + (loc - (TN - P)), 11);
   return gs_wait(cx, cx.rec.halo(I, ot, 2) + (jm - (g.N - P)), 12);
 }
 
+// U at nodes i0-P .. i0+NODES-1+P (global indices) for the Jacobian rows of a chunk: straight
+// loads inside this rank's slab, the generic path (wrap / clamp, another rank's words) at the
+// ends of the domain and of the slab
+template <int NODES>
+__device__ __forceinline__ void gs_load_windows(double (&win)[NF][NODES + 2 * P], int i0, GsCtx& cx,
+                                                const Geom& g, const Buf& b, const TfStepDesc& sd) {
+  const int lo = i0 - P, hi = i0 + NODES + P;
+  if (!GS_MULTI) {                 // one GPU: the pipeline's loader (neighbour-lane addresses)
+    load_windows<NODES, 0>(win, i0, g, b, 0, nullptr);
+    return;
+  }
+  if (lo >= cx.node_off && hi <= cx.node_off + cx.nodes_local && lo >= 0 && hi <= g.N) {
+#pragma unroll
+    for (int w = 0; w < NODES + 2 * P; ++w) win[0][w] = b.U[vidx(lo + w - cx.node_off, 0)];
+    return;
+  }
+#pragma unroll 1
+  for (int w = 0; w < NODES + 2 * P; ++w) {
+    const int j = lo + w;
+    // (beyond the padding of the last tile nothing is read: rows there are identity rows)
+    win[0][w] = (j < g.N + P) ? gs_node_value<0>(cx, g, b, map_node(j, g), sd) : 0.0;
+  }
+}
+
 // ------------------------------------------------------------------ factorisation
 // pass 1 of one chunk: its linear-fractional map (factor_body_stream of tf_kernels.cuh)
-__device__ __noinline__ void gs_factor_pass1(const Geom& g, const Buf& b, int chunk, double a,
-                                             const double* cst, Star& out, int& bad) {
+__device__ __noinline__ void gs_factor_pass1(const Geom& g, const Buf& b, GsCtx& cx, const TfStepDesc& sd,
+                                             int chunk, double a, const double* cst, Star& out, int& bad) {
   constexpr int NODES = M + EX;
   constexpr int NSB = C / BETA;
   const int i0 = chunk * M;
   const bool allreg = i0 >= P && i0 + NODES <= g.N - 2 * P;
   double win[NF][NODES + 2 * P];
-  load_windows<NODES, 0>(win, i0, g, b, 0, nullptr);
+  gs_load_windows<NODES>(win, i0, cx, g, b, sd);
   Star mine = Star::identity();
   double cur[BETA][WB], nxt[BETA][WB];
 #pragma unroll
@@ -417,7 +575,8 @@ __device__ __noinline__ void gs_factor_pass1(const Geom& g, const Buf& b, int ch
 
 // pass 2 of one chunk: elimination with the true incoming update X (in/out); U rows -> global,
 // L multipliers -> shared memory (own rows) / Lout (what is left on the next chunk's first rows)
-__device__ __noinline__ void gs_factor_pass2(const Geom& g, const Buf& b, const GsThread& th, int h,
+__device__ __noinline__ void gs_factor_pass2(const Geom& g, const Buf& b, GsCtx& cx, const TfStepDesc& sd,
+                                             const GsThread& th, int h,
                                              double a, const double* cst, double* sL, double* X,
                                              double (&Lout)[BETA][BETA], double* phiG, int& bad) {
   constexpr int NODES = M + EX;
@@ -426,7 +585,7 @@ __device__ __noinline__ void gs_factor_pass2(const Geom& g, const Buf& b, const 
   const int i0 = chunk * M;
   const bool allreg = i0 >= P && i0 + NODES <= g.N - 2 * P;
   double win[NF][NODES + 2 * P];
-  load_windows<NODES, 0>(win, i0, g, b, 0, nullptr);
+  gs_load_windows<NODES>(win, i0, cx, g, b, sd);
   double* Ug = b.Uf + th.cb(h) * (BETA + 1) - (long long)(th.cl + h) * BETA;   // row r, entry q: [(r*(BETA+1)+q)*32]
   double Lprev[BETA][BETA];
 #pragma unroll
@@ -497,16 +656,17 @@ __device__ __noinline__ void gs_factor_pass2(const Geom& g, const Buf& b, const 
 }
 
 __device__ __forceinline__ void gs_factor(const Geom& g, const Buf& b, GsCtx& cx, const GsThread& th,
-                                          double a, double* sL, double (&phiG)[GS_G][BETA * BETA]) {
+                                          const TfStepDesc& sd, double a, double* sL,
+                                          double (&phiG)[GS_G][BETA * BETA]) {
   GsShared& sh = *cx.sh;
   int bad = 0;
   Star mine = Star::identity();
   if (th.active) {
-    gs_factor_pass1(g, b, th.chunk0, a, sh.cst, mine, bad);
+    gs_factor_pass1(g, b, cx, sd, th.chunk0, a, sh.cst, mine, bad);
 #pragma unroll 1
     for (int h = 1; h < GS_G; ++h) {
       Star m1;
-      gs_factor_pass1(g, b, th.chunk0 + h, a, sh.cst, m1, bad);
+      gs_factor_pass1(g, b, cx, sd, th.chunk0 + h, a, sh.cst, m1, bad);
       mine = Star::combine(mine, m1);
     }
   }
@@ -524,7 +684,7 @@ __device__ __forceinline__ void gs_factor(const Geom& g, const Buf& b, GsCtx& cx
     double Lout[BETA][BETA];
 #pragma unroll 1
     for (int h = 0; h < GS_G; ++h) {
-      gs_factor_pass2(g, b, th, h, a, sh.cst, sL, X, Lout, phiG[h], bad);
+      gs_factor_pass2(g, b, cx, sd, th, h, a, sh.cst, sL, X, Lout, phiG[h], bad);
       // multipliers left on the next chunk's first BETA rows (entries q > r)
       const bool cross = (h == GS_G - 1) && (th.t == th.T - 1);
       if (!cross) {
@@ -558,9 +718,14 @@ __device__ __forceinline__ void gs_factor(const Geom& g, const Buf& b, GsCtx& cx
   if (g.periodic && threadIdx.x < NB * NB) {
     const double v = b.btab[2 * NB * NB + threadIdx.x];
     if (cx.tiles == 1) sh.ftop[threadIdx.x] = v;
-    else if (cx.tile == cx.tiles - 1) gs_post(cx, cx.rec.ftop() + threadIdx.x, v);
+    else if (cx.tile == cx.tiles - 1) gs_post(cx, cx.rec.ftop() + threadIdx.x, v);   // (own area)
   }
   GS_STAMP(3);
+}
+
+// address of (global row gr, entry q) in an array of this rank's slab
+__device__ __forceinline__ long long gs_fidx(const GsCtx& cx, int gr, int q, int width) {
+  return fidx(GS_MULTI ? gr - cx.node_off : gr, q, width);
 }
 
 // ------------------------------------------------------------------ border block
@@ -603,7 +768,7 @@ __device__ __forceinline__ void gs_gw_partial(const Geom& g, const Buf& b, GsCtx
           if (gr < g.nhat && (th_alive || (with_bottom && gr >= bot0))) {
             double gv[NB], wv[NB];
 #pragma unroll
-            for (int c = 0; c < NB; ++c) { gv[c] = b.Gb[fidx(gr, c, NB)]; wv[c] = b.Wb[fidx(gr, c, NB)]; }
+            for (int c = 0; c < NB; ++c) { gv[c] = b.Gb[gs_fidx(cx, gr, c, NB)]; wv[c] = b.Wb[gs_fidx(cx, gr, c, NB)]; }
 #pragma unroll
             for (int i = 0; i < NB; ++i)
 #pragma unroll
@@ -674,12 +839,12 @@ __device__ __noinline__ void gs_border_bottom(const Geom& g, const Buf& b, GsCtx
         const int jj = j - q;
         if (jj < 0) break;
         const double coef = isW ? gs_sl_at(sL, gr, q - 1, row0, cx.T)
-                                : b.Uf[fidx(gr - q, q, BETA + 1)] * b.Uf[fidx(gr - q, 0, BETA + 1)];
+                                : b.Uf[gs_fidx(cx, gr - q, q, BETA + 1)] * b.Uf[gs_fidx(cx, gr - q, 0, BETA + 1)];
         v -= coef * loc[jj];
       }
       loc[j] = v;
-      const double out = isW ? v : v * b.Uf[fidx(gr, 0, BETA + 1)];
-      ((isW ? b.Wb : b.Gb) + fidx(gr, c, NB))[0] = out;
+      const double out = isW ? v : v * b.Uf[gs_fidx(cx, gr, 0, BETA + 1)];
+      ((isW ? b.Wb : b.Gb) + gs_fidx(cx, gr, c, NB))[0] = out;
       (isW ? s_wbot : sh.gbot)[j * NB + c] = out;
     }
   }
@@ -1051,7 +1216,7 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
           for (int r = 0; r < C; ++r)
             if (r0 + r < bot0) {
 #pragma unroll
-              for (int c = 0; c < NB; ++c) acc[c] += b.Gb[fidx(r0 + r, c, NB)] * y[h][r];
+              for (int c = 0; c < NB; ++c) acc[c] += b.Gb[gs_fidx(cx, r0 + r, c, NB)] * y[h][r];
             }
         }
       }
@@ -1097,7 +1262,7 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
         for (int j = 0; j < NB; ++j) {                        // natural coupling of the last rows
           const int gr = bot0 + j;
           for (int c = 0; c < NB; ++c)
-            acc[c] = __fma_rn(tile_alive ? b.Gb[fidx(gr, c, NB)] : sh.gbot[j * NB + c], sh.yb[j], acc[c]);
+            acc[c] = __fma_rn(tile_alive ? b.Gb[gs_fidx(cx, gr, c, NB)] : sh.gbot[j * NB + c], sh.yb[j], acc[c]);
         }
         double ybv[NB];
         for (int c = 0; c < NB; ++c) ybv[c] = __dsub_rn(sh.yb[NB + c], acc[c]);
@@ -1130,7 +1295,7 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
           const int gr = r0 + r;
           if (gr < g.nhat && (th_alive || gr >= bot0)) {
 #pragma unroll
-            for (int c = 0; c < NB; ++c) y[h][r] = __fma_rn(-b.Wb[fidx(gr, c, NB)], xb[c], y[h][r]);
+            for (int c = 0; c < NB; ++c) y[h][r] = __fma_rn(-b.Wb[gs_fidx(cx, gr, c, NB)], xb[c], y[h][r]);
           } else if (gr >= g.nhat && gr < g.nhat + NB) {
 #pragma unroll
             for (int c = 0; c < NB; ++c) if (gr - g.nhat == c) y[h][r] = xb[c];
@@ -1240,20 +1405,50 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
       }
     }
   }
+  if (GS_MULTI && LAST && cx.nranks > 1 && th.active) {
+    // the state of the NEXT step at the tile edges: another rank's first phases read it as
+    // words (there is no kernel boundary between ranks); tagged with the next epoch
+#pragma unroll
+    for (int h = 0; h < GS_G; ++h) {
+      const int i0 = (th.chunk0 + h) * M;
+      const bool first = th.t == 0 && h == 0, lastc = th.t == T - 1 && h == GS_G - 1;
+      const bool tail = last_tile && i0 + M > g.N - P && i0 < g.N;
+      if (first || lastc || tail) {
+#pragma unroll 1
+        for (int r = 0; r < C; ++r) {
+          const int i = i0 + r;
+          const int loc = i - cx.tile * TN;
+          const bool e0 = loc < GS_HW, e1 = loc >= TN - P, e2 = last_tile && i >= g.N - P && i < g.N;
+          if (e0 || e1 || e2) {
+            const double nv = b.Un[th.cb(h) + (long long)r * 32];
+            const long long nt = (cx.tag >= (1 << 28)) ? 1 : cx.tag + 1;
+            if (e0) gs_post_tag(cx, cx.rec.halo(0, cx.tile, 0) + loc, nv, nt);
+            if (e1) gs_post_tag(cx, cx.rec.halo(0, cx.tile, 1) + (loc - (TN - P)), nv, nt);
+            if (e2) gs_post_tag(cx, cx.rec.halo(0, cx.tile, 2) + (i - (g.N - P)), nv, nt);
+          }
+        }
+      }
+    }
+  }
   if (!LAST) __syncthreads();       // k_I of the tile is in place before the next stage reads it
   GS_STAMP(9 + 6 * I);
 }
 
+}  // namespace GS_NS
 }  // namespace tfk
 
+#ifndef TF_GS_ONCE
 #ifndef TF_GS_MINB
 #define TF_GS_MINB 1
 #endif
 // (read by the host: chunks per thread, max threads per CTA)
 extern "C" __device__ int tf_gs_cfg[2] = {TF_GS_G, TF_GS_NT};
-extern "C" __global__ void __launch_bounds__(tfk::GS_NT, TF_GS_MINB) tf_k_gridstep(tfk::Geom g, tfk::Buf b,
-                                                                          TfStepDesc sd) {
+#endif
+// `g` describes the WHOLE grid (N, nhat, nblk of all ranks together); mr this rank's slab
+extern "C" __global__ void __launch_bounds__(tfk::GS_NT, TF_GS_MINB) TF_GS_KNAME(tfk::Geom g, tfk::Buf b,
+                                                                        TfStepDesc sd, TfGsMulti mr) {
   using namespace tfk;
+  using namespace tfk::GS_NS;
   extern __shared__ __align__(128) double dsm_gs[];
   __shared__ GsShared sh;
   const int T = blockDim.x;
@@ -1262,15 +1457,25 @@ extern "C" __global__ void __launch_bounds__(tfk::GS_NT, TF_GS_MINB) tf_k_gridst
   GsCtx cx;
   cx.rec.base = (LbWord*)b.gs;
   cx.rec.tiles = (int)gridDim.x;
+  cx.rec.nranks = mr.nranks;
+#pragma unroll
+  for (int r = 0; r < TF_GS_MAXRANKS; ++r) cx.rec.bases[r] = (LbWord*)mr.bases[r];
   cx.sh = &sh;
   cx.status = b.status;
-  cx.tile = (int)blockIdx.x;
-  cx.tiles = (int)gridDim.x;
+  cx.rank = GS_MULTI ? mr.rank : 0;
+  cx.nranks = GS_MULTI ? mr.nranks : 1;
+  cx.ltile = (int)blockIdx.x;
+  cx.tile = cx.rank * (int)gridDim.x + (int)blockIdx.x;
+  cx.tiles = GS_MULTI ? mr.tiles_total : (int)gridDim.x;
   cx.T = T;
+  cx.nodes_local = (int)gridDim.x * T * GS_G * M;
+  cx.node_off = cx.rank * cx.nodes_local;
   if (threadIdx.x == 0) {
     sh.epoch = ld_flag(b.ctl + 0);
     sh.abort = 0;
     sh.nalive = 0;
+    tf_gs_stuck[blockIdx.x & 1023] = 0;
+    if (blockIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tf_gs_when[0]));
   }
   for (int k = threadIdx.x; k < NC2; k += T) sh.cst[k] = b.cst[k];
   __syncthreads();
@@ -1279,15 +1484,21 @@ extern "C" __global__ void __launch_bounds__(tfk::GS_NT, TF_GS_MINB) tf_k_gridst
   th.t = (int)threadIdx.x;
   th.T = T;
   th.chunk0 = (cx.tile * T + th.t) * GS_G;
-  th.blk = th.chunk0 >> 5;
-  th.cl = th.chunk0 & 31;
-  th.active = th.blk < g.nblk;
+  {
+    const int lchunk0 = (cx.ltile * T + th.t) * GS_G;
+    th.blk = lchunk0 >> 5;
+    th.cl = lchunk0 & 31;
+  }
+  th.active = th.blk < mr.nblk_local;
   const double a = sd.a;
   GS_STAMP(0);
-  double phiG[GS_G][BETA * BETA];
-  gs_factor(g, b, cx, th, a, sL, phiG);
-  if (cx.tile == cx.tiles - 1) gs_border_bottom(g, b, cx, a, sL);
   double emax = 0.0;
+  // (tiles behind the last live one -- several GPUs, the grid does not fill the last slab --
+  //  hold padding only: nothing to do but the bookkeeping at the end)
+  if (cx.tile < cx.tiles) {
+  double phiG[GS_G][BETA * BETA];
+  gs_factor(g, b, cx, th, sd, a, sL, phiG);
+  if (cx.tile == cx.tiles - 1) gs_border_bottom(g, b, cx, a, sL);
   bool th_alive = false, tile_alive = false;
   switch (sd.s) {
     case 1:
@@ -1303,6 +1514,7 @@ extern "C" __global__ void __launch_bounds__(tfk::GS_NT, TF_GS_MINB) tf_k_gridst
       gs_stage<2, true>(g, b, cx, th, sd, a, sL, sS, phiG, th_alive, tile_alive, emax);
       break;
   }
+  }
   // error estimate: per-tile maximum, reduced by the last CTA to finish
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -1315,13 +1527,13 @@ extern "C" __global__ void __launch_bounds__(tfk::GS_NT, TF_GS_MINB) tf_k_gridst
   if (threadIdx.x == 0) {
     for (int w = 1; w < (T >> 5); ++w) emax = (sh.err[w] > emax || sh.err[w] != sh.err[w]) ? sh.err[w] : emax;
     double* errt = cx.rec.errt();
-    errt[cx.tile] = emax;
+    errt[cx.ltile] = emax;
     __threadfence();
     const unsigned d = atomicAdd((unsigned*)(b.ctl + 2), 1u);
     if (d == gridDim.x - 1) {
       __threadfence();
       double e = 0.0;
-      for (int t = 0; t < cx.tiles; ++t) {
+      for (int t = 0; t < (int)gridDim.x; ++t) {
         const double v = __ldcg(errt + t);
         e = (v > e || v != v) ? v : e;
       }
@@ -1332,4 +1544,36 @@ extern "C" __global__ void __launch_bounds__(tfk::GS_NT, TF_GS_MINB) tf_k_gridst
   }
 }
 
+#if TF_GS_MULTI
+// Several GPUs, after an upload: the stage-0 words of this rank's tile edges from U (every later
+// step gets them from the last stage of the step before)
+extern "C" __global__ void tf_k_gs_seed(tfk::Geom g, tfk::Buf b, TfGsMulti mr, int tiles_local, int T) {
+  using namespace tfk;
+  using namespace tfk::GS_NS;
+  GsRec rec;
+  rec.base = (LbWord*)b.gs;
+  rec.tiles = tiles_local;
+  rec.nranks = 1;                                 // own area, local tile indices
+  const long long tag = ld_flag(b.ctl + 0);
+  const int TN = T * GS_G * M;
+  const int node_off = mr.rank * tiles_local * TN;
+  const int k = threadIdx.x;
+  if (k >= GS_HW) return;
+  for (int lt = blockIdx.x; lt < tiles_local; lt += gridDim.x) {
+    const int first = node_off + lt * TN;
+    if (first + k < g.N) st_word_sys(rec.halo(0, lt, 0) + k, b.U[vidx(lt * TN + k, 0)], tag);
+    if (k >= P) continue;
+    if (first + TN - P + k < g.N)
+      st_word_sys(rec.halo(0, lt, 1) + k, b.U[vidx(lt * TN + TN - P + k, 0)], tag);
+    const int last = g.N - P + k;                 // the last P real nodes of the whole grid
+    if (last >= first && last < first + TN) st_word_sys(rec.halo(0, lt, 2) + k, b.U[vidx(last - node_off, 0)], tag);
+  }
+}
+#endif
+
+#undef GS_NS
+#undef TF_GS_KNAME
+#ifndef TF_GS_ONCE
+#define TF_GS_ONCE 1
+#endif
 #endif  // V == 1 && no helper fields

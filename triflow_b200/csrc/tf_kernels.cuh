@@ -1754,7 +1754,12 @@ TF_BWD_KERNEL(tf_k_bwd2l, 2, 1)
 TF_BWD_KERNEL(tf_k_bwdg, -1, -1)
 
 #include "tf_sysstep.cuh"
-#include "tf_gridstep.cuh"
+#define TF_GS_MULTI 0
+#include "tf_gridstep.cuh"      // tf_k_gridstep: one GPU
+#undef TF_GS_MULTI
+#define TF_GS_MULTI 1
+#include "tf_gridstep.cuh"      // tf_k_gridstep_mr, tf_k_gs_seed: one grid over several GPUs
+#undef TF_GS_MULTI
 
 // Dirichlet-style hook: U[var][0] = left, U[var][N-1] = right  (README.md:126-129)
 extern "C" __global__ void tf_k_dirichlet(Geom g, double* __restrict__ U, const double* __restrict__ dir,

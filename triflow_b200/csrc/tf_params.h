@@ -61,6 +61,16 @@ struct TfStage {
 };
 
 
+/* One grid over several GPUs (tf_gridstep.cuh): every rank owns a slab of whole tiles. */
+#define TF_GS_MAXRANKS 8
+struct TfGsMulti {
+  void* bases[TF_GS_MAXRANKS];   /* record areas of all ranks (own + IPC-mapped peers) */
+  int rank, nranks;
+  int nblk_local;                /* warp-blocks that hold data on this rank */
+  int tiles_total;               /* live tiles of the whole grid (<= nranks x tiles per rank; the
+                                    tiles behind them hold padding only and do nothing) */
+};
+
 /* Whole-step descriptor of the system-resident kernel (tf_sysstep.cuh): every stage of
    one ROW_general._fixed_step / Theta step (reference core/schemes.py:142-174,548-559). */
 struct TfStepDesc {
