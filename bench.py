@@ -359,6 +359,11 @@ def run_gpu(args):
                 extras[other] = quick_measure(other, min(args.steps, 10))
             except Exception as e:  # noqa: BLE001  (never lose the headline line)
                 extras[other] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    if ws > 1 and args.others:
+        try:                                    # every rank takes part
+            extras["ks_one_grid"] = slab_measure(ws, min(args.steps, 10))
+        except Exception as e:  # noqa: BLE001
+            extras["ks_one_grid"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     cpu = None
     if rank == 0 and ws == 1 and not args.no_cpu:
         try:
@@ -382,6 +387,44 @@ def run_gpu(args):
         }
         _emit(out)
     D.finalize()
+
+
+def slab_measure(ws, steps):
+    """ONE Kuramoto-Sivashinsky grid of ws x 2^20 nodes stepped by all GPUs together (SURVEY K7:
+    slab per GPU, halo / scan / border words read from the peer GPU over NVLink inside the step
+    kernel).  Every rank calls this; device-timed with CUDA events, max over ranks."""
+    import ctypes
+    from triflow_b200 import _lib, distributed as D
+    from triflow_b200.model import Model
+    wk = WORKLOADS["ks"]
+    N = ws << 20
+    c = W.kuramoto(N)
+    model = Model(**W.model_args("ks"), compiler="cuda")
+    from triflow_b200 import schemes as S
+    scheme = S.ROS3PRw(model, time_stepping=False)
+    g = D.SlabGrid(model, scheme, c["x"], c["fields"], c["pars"])
+    lib, ctx = _lib.lib(), model._cuda.ctx
+    g.step(c["dt"], 3)
+    g.sync()
+    D.barrier()
+    _lib.check(lib.tf_ctx_timer_start(ctx))
+    g.step(c["dt"], steps)
+    ms = ctypes.c_float()
+    _lib.check(lib.tf_ctx_timer_stop(ctx, ctypes.byref(ms)))
+    g.sync()
+    t = D.max_over_ranks(ms.value * 1e-3)
+    local = g.download()
+    ok = bool(np.isfinite(local).all())
+    tiles = (g.states[0].tiles_local, g.states[0].tiles_total)
+    g.close()
+    peak, _ = peaks()
+    rate = float(N) * steps / t
+    return {"config": "configs[2] x %d: one grid over %d GPUs" % (ws, ws), "pde": "ks", "scheme": wk["scheme"],
+            "nodes": N, "value": rate, "ms_per_step": t * 1e3 / steps, "finite": ok,
+            "tiles_per_gpu": tiles[0], "tiles": tiles[1],
+            "exchange": "tagged 16-byte words read from the peer GPU's record area over NVLink inside "
+                        "the step kernel (no collective)",
+            "bytes_per_node_step": wk["Q"], "step_frac_of_all_gpus": round(wk["Q"] * rate / 1e9 / (peak * ws), 4)}
 
 
 def quick_measure(workload, steps):

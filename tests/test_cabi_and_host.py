@@ -111,6 +111,50 @@ if rank == 0:
     assert "GATHER_OK" in out.stdout
 
 
+def test_slab_partition_covers_the_grid():
+    """Slabs of whole tiles: consecutive, disjoint, cover [0, N); only the tail may be short."""
+    from triflow_b200.distributed import slab_partition
+    for N, nranks, tn, tl in ((2097152, 2, 3584, 293), (4194304, 4, 3584, 293), (20000, 2, 2048, 5),
+                              (50001, 2, 2048, 13), (8388608, 8, 3584, 293)):
+        part = slab_partition(N, nranks, tn, tl)
+        assert len(part) == nranks and part[0][0] == 0
+        for r in range(1, nranks):
+            assert part[r][0] == part[r - 1][0] + part[r - 1][1] == r * tl * tn
+        assert sum(n for _, n in part) == N and all(n > 0 for _, n in part)
+
+
+def test_two_rank_gloo_slab_gather():
+    """world_size 2 on CPU (gloo): the final gather of a slab grid (ragged last slab)."""
+    script = r'''
+import os, sys, numpy as np
+sys.path.insert(0, %r)
+from triflow_b200 import distributed as D
+rank, ws = D.init("gloo")
+part = D.slab_partition(50001, ws, 2048, 13)
+off, n = part[rank]
+full = D.gather_slabs(np.arange(off, off + n, dtype=float), part)
+try:
+    D.gather_slabs(np.zeros(3), part)
+    raise SystemExit("a slab of the wrong size was accepted")
+except ValueError:
+    pass
+if rank == 0:
+    assert full.shape == (50001,) and (full == np.arange(50001)).all()
+    print("SLAB_GATHER_OK")
+''' % ROOT
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29573")
+    out = subprocess.run([sys.executable, "-c",
+                          "import subprocess,sys,os;"
+                          "ps=[subprocess.Popen([sys.executable,'-c',%r],env=dict(os.environ,"
+                          "RANK=str(r),WORLD_SIZE='2',LOCAL_RANK=str(r)),stdout=subprocess.PIPE,"
+                          "text=True) for r in range(2)];"
+                          "outs=[p.communicate()[0] for p in ps];"
+                          "print(''.join(outs)); sys.exit(max(p.returncode for p in ps))" % script],
+                         env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "SLAB_GATHER_OK" in out.stdout
+
+
 def test_host_pipeline_member_slicing():
     """HostPipeline splits fields / parameters along the member axis only."""
     from triflow_b200.ensemble import _members

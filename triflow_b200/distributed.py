@@ -108,6 +108,31 @@ def slab_partition(N, nranks, tile_nodes, tiles_local):
     return out
 
 
+def gather_slabs(local, partition):
+    """Final gather of a slab grid: rank r holds ``partition[r][1]`` consecutive nodes starting
+    at ``partition[r][0]``.  Returns the whole grid on rank 0, ``None`` elsewhere."""
+    import torch
+    import torch.distributed as dist
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    rank, ws = dist.get_rank(), dist.get_world_size()
+    if local.size != partition[rank][1]:
+        raise ValueError("rank %d holds %d nodes, its slab has %d" % (rank, local.size, partition[rank][1]))
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    nmax = max(n for _, n in partition)
+    buf = torch.zeros(nmax, dtype=torch.float64, device=dev)
+    buf[:local.size] = torch.from_numpy(local).to(dev)
+    out = [torch.empty_like(buf) for _ in range(ws)] if rank == 0 else None
+    dist.gather(buf, out, dst=0)
+    if rank != 0:
+        return None
+    full = np.concatenate([o[:n].cpu().numpy() for o, (_, n) in zip(out, partition)])
+    offs = [off for off, _ in partition]
+    assert offs == sorted(offs) and offs[0] == 0
+    return full
+
+
 class _SlabState:
     """This rank's slab of a grid spread over several GPUs (``tf_state_create_slab``)."""
 
@@ -265,17 +290,7 @@ class SlabGrid:
         local = self.download()
         if self._local or self.nranks == 1:
             return local
-        import torch
-        import torch.distributed as dist
-        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-        nmax = max(n for _, n in self.partition())
-        buf = torch.zeros(nmax, dtype=torch.float64, device=dev)
-        buf[:local.size] = torch.from_numpy(local).to(dev)
-        out = [torch.empty_like(buf) for _ in range(self.nranks)] if self.rank == 0 else None
-        dist.gather(buf, out, dst=0)
-        if self.rank != 0:
-            return None
-        return np.concatenate([o[:n].cpu().numpy() for o, (_, n) in zip(out, self.partition())])
+        return gather_slabs(local, self.partition())
 
     def partition(self):
         """``[(node_off, n_local)]`` of every rank."""
