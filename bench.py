@@ -285,6 +285,10 @@ def run_gpu(args):
 
     # -- final gather of the states to rank 0 (the only inter-GPU traffic of an ensemble)
     h_final = _lib.pinned_empty((batch, N * model._nvar))
+    if args.workload == "ensemble" and ws > 1:
+        # the first collective of a process group builds the NCCL communicator (hundreds of
+        # ms): not part of the gather
+        D.gather_members(np.zeros((batch, 1)), args.members)
     D.barrier()
     t0 = time.perf_counter()
     u_local = ens.download(out=h_final)

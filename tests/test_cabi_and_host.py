@@ -166,3 +166,18 @@ def test_host_pipeline_member_slicing():
     assert _members(per_node, 2, 5, batch, N) is per_node
     assert np.array_equal(_members(full, 2, 5, batch, N), full[2:5])
     assert _members(0.25, 2, 5, batch, N) == 0.25
+
+
+def test_value_layout_classification():
+    """1-D values: one per member or one per node; ambiguous when batch == N."""
+    import pytest
+    from triflow_b200.compiler import value_kind
+    assert value_kind((), 4, 10) == "scalar"
+    assert value_kind((4,), 4, 10) == "member" and value_kind((10,), 4, 10) == "node"
+    assert value_kind((4, 10), 4, 10) == "member_node" and value_kind((4, 1), 4, 10) == "member"
+    assert value_kind((1, 10), 4, 10) == "node" and value_kind((10,), 1, 10) == "node"
+    assert value_kind((10, 1), 10, 10) == "member" and value_kind((1, 10), 10, 10) == "node"
+    with pytest.raises(ValueError, match="ambiguous"):
+        value_kind((10,), 10, 10)
+    with pytest.raises(ValueError):
+        value_kind((7,), 4, 10)

@@ -55,15 +55,23 @@ def build_library(force=False):
     srcs = [os.path.join(CSRC, "tf_host.cu"), os.path.join(CSRC, "tf_params.h"),
             os.path.join(os.path.dirname(HERE), "include", "triflow_b200.h")]
     stamp = LIB_PATH + ".stamp"
+    flags = ["-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", *ARCH,
+             "-lineinfo", "-diag-suppress", "177"]
     digest = _sources_digest(srcs)
     if (not force and os.path.exists(LIB_PATH) and os.path.exists(stamp)
-            and open(stamp).read() == digest):
+            and open(stamp).read().split("|")[0] == digest):
         return LIB_PATH
-    cmd = [_nvcc(), "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-cudart",
-           "static", *ARCH, "-lineinfo", "-diag-suppress", "177", "-o", LIB_PATH, srcs[0]]
-    subprocess.check_call(cmd)
-    with open(stamp, "w") as f:
-        f.write(digest)
+    try:
+        ver = subprocess.run([_nvcc(), "--version"], capture_output=True, text=True).stdout.split()[-1]
+    except Exception:  # noqa: BLE001
+        ver = "?"
+    # several ranks may build at once on a fresh checkout: private temporary, atomic rename
+    tmp = "%s.tmp%d" % (LIB_PATH, os.getpid())
+    subprocess.check_call([_nvcc(), *flags, "-o", tmp, srcs[0]])
+    os.replace(tmp, LIB_PATH)
+    with open(stamp + ".tmp%d" % os.getpid(), "w") as f:
+        f.write("%s|%s|%s" % (digest, " ".join(flags), ver))
+    os.replace(stamp + ".tmp%d" % os.getpid(), stamp)
     return LIB_PATH
 
 

@@ -246,8 +246,10 @@ class Lowered:
         ns = _host_namespace()
         ns["dx"] = np.float64(dx)
         for name in self.uniform_pars:
-            ns[name] = np.broadcast_to(
-                np.asarray(pars[name], dtype=np.float64), (batch,)).copy()
+            v = np.asarray(pars[name], dtype=np.float64)
+            if v.ndim == 2 and v.shape[1] == 1:           # (batch, 1): one value per member
+                v = v[:, 0]
+            ns[name] = np.broadcast_to(v, (batch,)).copy()
         table = np.empty((batch, 2 * max(1, self.n_const)), dtype=np.float64)
         table[:] = 1.0
         with np.errstate(all="ignore"):

@@ -18,6 +18,7 @@ fused factor / solve kernels; they find the compiled model through
 """
 
 import ctypes as C
+import os
 
 import numpy as np
 from scipy.sparse import csc_matrix
@@ -26,11 +27,37 @@ from . import _lib, codegen
 
 
 def default_chunk_nodes(nvar, half_width):
+    if os.environ.get("TF_CHUNK_NODES"):            # tuning knob
+        return int(os.environ["TF_CHUNK_NODES"])
     beta = half_width * nvar + nvar - 1
     m = 8
     while m * nvar > 8 and m > 1 and (m // 2) * nvar >= beta:
         m //= 2
     return m
+
+
+def value_kind(shape, batch, N, name="value"):
+    """How a parameter / field value is laid out for ``batch`` systems of ``N`` nodes:
+    ``"scalar"``, ``"member"`` (one value per system), ``"node"`` (per node, shared) or
+    ``"member_node"``.  A 1-D array is ambiguous when ``batch == N``: say which with a
+    ``(batch, 1)`` or ``(1, N)`` shape."""
+    shape = tuple(shape)
+    if len(shape) == 0:
+        return "scalar"
+    if len(shape) == 1:
+        if batch > 1 and batch == N and shape[0] == N:
+            raise ValueError("%s: a 1-D array of length %d is ambiguous when batch == N; pass "
+                             "shape (batch, 1) for one value per member or (1, N) per node" % (name, N))
+        if batch > 1 and shape[0] == batch:
+            return "member"
+        if shape[0] == N:
+            return "node"
+    elif len(shape) == 2 and shape[0] in (1, batch):
+        if shape[1] == 1:
+            return "member" if shape[0] == batch and batch > 1 else "scalar"
+        if shape[1] == N:
+            return "member_node" if shape[0] == batch and batch > 1 else "node"
+    raise ValueError("%s: shape %s fits neither the batch (%d) nor the grid (%d)" % (name, shape, batch, N))
 
 
 class DeviceState:
@@ -167,13 +194,8 @@ class CompiledModel:
         system (uniform inside a system); (N,) / (batch, N) arrays are per node."""
         out = []
         for p in self.model._pars:
-            shp = np.shape(pars[p])
-            if len(shp) == 0 or (batch > 1 and shp == (batch,)):
-                continue
-            if shp[-1] != N:
-                raise ValueError("parameter %r: shape %s fits neither the batch (%d) "
-                                 "nor the grid (%d)" % (p, shp, batch, N))
-            out.append(p)
+            if value_kind(np.shape(pars[p]), batch, N, "parameter %r" % p) in ("node", "member_node"):
+                out.append(p)
         return tuple(out)
 
     def variant(self, node_pars=()):

@@ -35,6 +35,9 @@ class Ensemble:
                 if np.ndim(v) == 2 or (np.ndim(v) == 1 and np.shape(v)[0] != N):
                     batch = max(batch, np.shape(v)[0])
         self.batch, self.N = int(batch), N
+        from .compiler import value_kind
+        for name, v in list(fields.items()) + [(p, pars[p]) for p in model._pars]:
+            value_kind(np.shape(v), self.batch, N, name)       # raises on ambiguous / bad shapes
         self.nvar = model._nvar
         self.pars = dict(pars)
         self.state = cm.new_state(pars, N, self.batch, bool(pars["periodic"]), ctx=ctx)
@@ -149,9 +152,8 @@ class Ensemble:
 
 def _members(v, lo, hi, batch, N):
     """Slice the member axis of a field / parameter value (same shapes as Ensemble)."""
-    if np.ndim(v) == 2:
-        return np.asarray(v)[lo:hi]
-    if np.ndim(v) == 1 and np.shape(v)[0] == batch and batch != N:
+    from .compiler import value_kind
+    if value_kind(np.shape(v), batch, N) in ("member", "member_node"):
         return np.asarray(v)[lo:hi]
     return v
 

@@ -185,8 +185,8 @@ class LazyFields:
 
     # everything else is the container API, after materialisation
     def __getitem__(self, key):
-        if key == "x" or key in self._template.helper_functions:
-            return self._template[key]
+        if self._real is None and (key == "x" or key in self._template.helper_functions):
+            return self._template[key]           # no download needed for grid / helper fields
         return self._load()[key]
 
     def __setitem__(self, key, value):
