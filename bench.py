@@ -168,8 +168,12 @@ def build_problem(name, members, N=None):
     from triflow_b200 import schemes as S
     if name == "ensemble":
         c = W.ensemble(N or 4096, members)
+        # one value per member, in the unambiguous (batch, 1) form: with 4096 members per GPU
+        # (cfg 5 on 8 GPUs) a (batch,) array would have the length of the grid
+        pars = {k: (np.asarray(v, dtype=float).reshape(-1, 1) if np.ndim(v) == 1 else v)
+                for k, v in c["pars"].items()}
         return ("advdiff", lambda m: S.ROS3PRw(m, time_stepping=False), c["x"], c["fields"],
-                c["pars"], S.Dirichlet(U=(1.0, 0.0)), len(c["members"]), c["x"].size, c["dt"])
+                pars, S.Dirichlet(U=(1.0, 0.0)), len(c["members"]), c["x"].size, c["dt"])
     if name == "ks":
         c = W.kuramoto(N or 2 ** 20)
         return ("ks", lambda m: S.ROS3PRw(m, time_stepping=False), c["x"], c["fields"],

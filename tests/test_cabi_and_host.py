@@ -166,6 +166,13 @@ def test_host_pipeline_member_slicing():
     assert _members(per_node, 2, 5, batch, N) is per_node
     assert np.array_equal(_members(full, 2, 5, batch, N), full[2:5])
     assert _members(0.25, 2, 5, batch, N) == 0.25
+    # batch == N: fields are per node, parameters must say what they are
+    sq = np.arange(N, dtype=float)
+    assert _members(sq, 2, 5, N, N, field=True) is sq
+    assert np.array_equal(_members(sq[:, None], 2, 5, N, N), sq[2:5, None])
+    import pytest
+    with pytest.raises(ValueError, match="ambiguous"):
+        _members(sq, 2, 5, N, N)
 
 
 def test_value_layout_classification():

@@ -678,6 +678,39 @@ def test_ensemble_per_member_adaptive_controller():
     assert (ens2.failed == 3).all()
 
 
+def test_ensemble_with_as_many_members_as_nodes():
+    """batch == N (BASELINE cfg 5 on 8 GPUs: 4096 members of 4096 nodes per GPU): per-member
+    parameters in the explicit (batch, 1) form mean the same to Ensemble and HostPipeline, a
+    bare (batch,) array is refused."""
+    from triflow_b200 import _lib, schemes as S, workloads as W
+    from triflow_b200.ensemble import Ensemble, HostPipeline
+    N = 256
+    m = gmodel("advdiff")
+    sch = S.ROS3PRw(m, **FX)
+    hook = S.Dirichlet(U=(1.0, 0.0))
+    cw = W.ensemble(N, np.arange(N + 1) * 97 % 32768)            # N + 1 members: unambiguous
+    wide = Ensemble(m, sch, cw["x"], cw["fields"], cw["pars"], hook=hook, batch=N + 1)
+    wide.step(cw["dt"], 5)
+    ref = wide.download()[:N]
+    wide.state.close()
+    pars = dict(k=cw["pars"]["k"][:N, None], c=cw["pars"]["c"][:N, None], periodic=False)
+    with pytest.raises(ValueError, match="ambiguous"):
+        Ensemble(m, sch, cw["x"], cw["fields"], dict(pars, k=cw["pars"]["k"][:N]), hook=hook, batch=N)
+    ens = Ensemble(m, sch, cw["x"], cw["fields"], pars, hook=hook, batch=N)
+    ens.step(cw["dt"], 5)
+    assert np.array_equal(ens.download(), ref)
+    ens.state.close()
+    pipe = HostPipeline(m, sch, cw["x"], cw["fields"], pars, hook=hook, batch=N, groups=4)
+    h_in = np.repeat(np.asarray(cw["fields"]["U"])[None], N, axis=0).copy()
+    h_out = np.empty_like(h_in)
+    for _ in range(5):
+        pipe.step_host(h_in, h_out, cw["dt"])
+        pipe.sync()
+        h_in, h_out = h_out, h_in
+    assert np.array_equal(h_in, ref)
+    pipe.close()
+
+
 def test_host_pipeline_equals_blocking_ensemble():
     """upload -> step -> download pipelined over member blocks (asynchronous contexts)
     gives bit-identical results to the blocking Ensemble calls, for uneven blocks too."""

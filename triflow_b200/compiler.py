@@ -36,15 +36,17 @@ def default_chunk_nodes(nvar, half_width):
     return m
 
 
-def value_kind(shape, batch, N, name="value"):
+def value_kind(shape, batch, N, name="value", field=False):
     """How a parameter / field value is laid out for ``batch`` systems of ``N`` nodes:
     ``"scalar"``, ``"member"`` (one value per system), ``"node"`` (per node, shared) or
-    ``"member_node"``.  A 1-D array is ambiguous when ``batch == N``: say which with a
-    ``(batch, 1)`` or ``(1, N)`` shape."""
+    ``"member_node"``.  A 1-D PARAMETER array is ambiguous when ``batch == N``: say which with
+    a ``(batch, 1)`` or ``(1, N)`` shape (a 1-D ``field`` is a function on the grid: per node)."""
     shape = tuple(shape)
     if len(shape) == 0:
         return "scalar"
     if len(shape) == 1:
+        if field and shape[0] == N:
+            return "node"
         if batch > 1 and batch == N and shape[0] == N:
             raise ValueError("%s: a 1-D array of length %d is ambiguous when batch == N; pass "
                              "shape (batch, 1) for one value per member or (1, N) per node" % (name, N))

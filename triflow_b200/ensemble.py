@@ -36,8 +36,10 @@ class Ensemble:
                     batch = max(batch, np.shape(v)[0])
         self.batch, self.N = int(batch), N
         from .compiler import value_kind
-        for name, v in list(fields.items()) + [(p, pars[p]) for p in model._pars]:
-            value_kind(np.shape(v), self.batch, N, name)       # raises on ambiguous / bad shapes
+        for name, v in fields.items():                         # raises on ambiguous / bad shapes
+            value_kind(np.shape(v), self.batch, N, name, field=True)
+        for name in model._pars:
+            value_kind(np.shape(pars[name]), self.batch, N, name)
         self.nvar = model._nvar
         self.pars = dict(pars)
         self.state = cm.new_state(pars, N, self.batch, bool(pars["periodic"]), ctx=ctx)
@@ -150,10 +152,10 @@ class Ensemble:
         _lib.check(_lib.lib().tf_ctx_sync(self.state.ctx))
 
 
-def _members(v, lo, hi, batch, N):
+def _members(v, lo, hi, batch, N, field=False):
     """Slice the member axis of a field / parameter value (same shapes as Ensemble)."""
     from .compiler import value_kind
-    if value_kind(np.shape(v), batch, N) in ("member", "member_node"):
+    if value_kind(np.shape(v), batch, N, field=field) in ("member", "member_node"):
         return np.asarray(v)[lo:hi]
     return v
 
@@ -185,7 +187,7 @@ class HostPipeline:
         self.parts = []
         for lo, hi in self.ranges:
             ctx = _lib.new_context()
-            f = {k: _members(v, lo, hi, self.batch, N) for k, v in fields.items()}
+            f = {k: _members(v, lo, hi, self.batch, N, field=True) for k, v in fields.items()}
             p = {k: (_members(v, lo, hi, self.batch, N) if k != "periodic" else v)
                  for k, v in pars.items()}
             part = Ensemble(model, scheme, x, f, p, hook=hook, batch=hi - lo, ctx=ctx)
