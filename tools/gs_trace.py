@@ -25,10 +25,10 @@ e = Ensemble(m, mk(m), c["x"], c["fields"], c["pars"], batch=1)
 e.set_fusion("grid")
 e.step(c["dt"], 6)
 e.sync()
-buf = np.zeros(256 * 32, dtype=np.uint64)
+buf = np.zeros(512 * 32, dtype=np.uint64)
 _lib.check(_lib.lib().tf_model_read_symbol(e.state.variant.handle, b"tf_gs_trace",
                                            buf.ctypes.data_as(ctypes.c_void_p), buf.nbytes))
-tr = buf.reshape(256, 32).astype(np.int64)
+tr = buf.reshape(512, 32).astype(np.int64)
 tiles = int((tr[:, 0] > 0).sum())
 tr = tr[:tiles]
 t0 = tr[:, 0].min()
@@ -45,3 +45,5 @@ for k in range(1, 4 + 6 * s):
                                                np.median(tr[:, k] - t0) / 1e3))
 print("start skew: %.2f us; slowest tiles by end time: %s" % (
     (tr[:, 0].max() - t0) / 1e3, np.argsort(tr[:, 3 + 6 * s])[-5:].tolist()))
+if len(sys.argv) > 3:
+    np.save(sys.argv[3], tr - t0)          # per-tile stamps (ns from the first start) for offline analysis

@@ -69,8 +69,8 @@
 // Optional per-tile phase time stamps (cubin built with -DTF_GS_TRACE; tools/gs_trace.py):
 // globaltimer ns of thread 0 at the phase boundaries of the last step.
 #ifdef TF_GS_TRACE
-__device__ unsigned long long tf_gs_trace[256 * 32];
-#define GS_STAMP(ph) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tf_gs_trace[(cx.tile & 255) * 32 + (ph)] = t_; } } while (0)
+__device__ unsigned long long tf_gs_trace[512 * 32];
+#define GS_STAMP(ph) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tf_gs_trace[(cx.tile & 511) * 32 + (ph)] = t_; } } while (0)
 #else
 #define GS_STAMP(ph) do { } while (0)
 #endif
