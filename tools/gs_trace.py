@@ -45,5 +45,9 @@ for k in range(1, 4 + 6 * s):
                                                np.median(tr[:, k] - t0) / 1e3))
 print("start skew: %.2f us; slowest tiles by end time: %s" % (
     (tr[:, 0].max() - t0) / 1e3, np.argsort(tr[:, 3 + 6 * s])[-5:].tolist()))
+if tr[:, 22].max() > 0:
+    late = (tr[:, 22] - tr[:, 1]) / 1e3
+    print("factor pass 1, latest thread of a tile behind thread 0: med %.2f max %.2f us (tile %d)" % (
+        np.median(late), late.max(), int(late.argmax())))
 if len(sys.argv) > 3:
     np.save(sys.argv[3], tr - t0)          # per-tile stamps (ns from the first start) for offline analysis

@@ -71,8 +71,11 @@
 #ifdef TF_GS_TRACE
 __device__ unsigned long long tf_gs_trace[512 * 32];
 #define GS_STAMP(ph) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tf_gs_trace[(cx.tile & 511) * 32 + (ph)] = t_; } } while (0)
+// (latest thread of the tile instead of thread 0)
+#define GS_STAMP_MAX(ph) do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMax(&tf_gs_trace[(cx.tile & 511) * 32 + (ph)], t_); } while (0)
 #else
 #define GS_STAMP(ph) do { } while (0)
+#define GS_STAMP_MAX(ph) do { } while (0)
 #endif
 
 // where every tile of an aborted launch was waiting (wait site, 0: not waiting); read by
@@ -293,6 +296,27 @@ __device__ __noinline__ double gs_wait(GsCtx& cx, const LbWord* p, int site) {
     if (gs_aborted(cx, ++spins, site)) return 0.0;
   }
 }
+// n consecutive words in ONE round trip per poll (all loads issued before any tag is compared)
+template <int N_>
+__device__ __noinline__ void gs_wait_many(GsCtx& cx, const LbWord* p, double (&out)[N_], int site) {
+  int spins = 0;
+  while (true) {
+    long long t[N_];
+#pragma unroll
+    for (int k = 0; k < N_; ++k) {
+      if (GS_MULTI && cx.nranks > 1) ld_word_sys(p + k, out[k], t[k]); else ld_word(p + k, out[k], t[k]);
+    }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < N_; ++k) ok = ok && (t[k] == cx.tag);
+    if (ok) return;
+    if (gs_aborted(cx, ++spins, site)) {
+#pragma unroll
+      for (int k = 0; k < N_; ++k) out[k] = 0.0;
+      return;
+    }
+  }
+}
 __device__ __forceinline__ void gs_post_tag(GsCtx& cx, LbWord* p, double v, long long tag) {
   if (GS_MULTI && cx.nranks > 1) st_word_sys(p, v, tag); else st_word(p, v, tag);
 }
@@ -509,11 +533,41 @@ __device__ __forceinline__ void gs_load_windows(double (&win)[NF][NODES + 2 * P]
     for (int w = 0; w < NODES + 2 * P; ++w) win[0][w] = b.U[vidx(lo + w - cx.node_off, 0)];
     return;
   }
+  // ends of the domain / of the slab: own nodes from memory, another rank's as words -- all
+  // words of the window polled together (one NVLink round trip per poll, not one per node)
+  const LbWord* wp[NODES + 2 * P];
+  const int TN = cx.T * GS_G * M;
 #pragma unroll 1
   for (int w = 0; w < NODES + 2 * P; ++w) {
     const int j = lo + w;
+    wp[w] = nullptr;
+    win[0][w] = 0.0;
     // (beyond the padding of the last tile nothing is read: rows there are identity rows)
-    win[0][w] = (j < g.N + P) ? gs_node_value<0>(cx, g, b, map_node(j, g), sd) : 0.0;
+    if (j >= g.N + P) continue;
+    const int jm = map_node(j, g);
+    if (jm >= cx.node_off && jm < cx.node_off + cx.nodes_local) {
+      win[0][w] = b.U[vidx(jm - cx.node_off, 0)];
+      continue;
+    }
+    const int ot = jm / TN, loc = jm - ot * TN;
+    wp[w] = (loc < GS_HW) ? cx.rec.halo(0, ot, 0) + loc
+          : (loc >= TN - P) ? cx.rec.halo(0, ot, 1) + (loc - (TN - P))
+                            : cx.rec.halo(0, ot, 2) + (jm - (g.N - P));
+  }
+  int spins = 0;
+  while (true) {
+    bool ok = true;
+#pragma unroll 1
+    for (int w = 0; w < NODES + 2 * P; ++w)
+      if (wp[w] != nullptr) {
+        long long t;
+        double v;
+        ld_word_sys(wp[w], v, t);
+        if (t == cx.tag) { win[0][w] = v; wp[w] = nullptr; }
+        else ok = false;
+      }
+    if (ok) break;
+    if (gs_aborted(cx, ++spins, 14)) break;
   }
 }
 
@@ -524,17 +578,21 @@ __device__ __noinline__ void gs_factor_pass1(const Geom& g, const Buf& b, GsCtx&
   constexpr int NODES = M + EX;
   constexpr int NSB = C / BETA;
   const int i0 = chunk * M;
-  const bool allreg = i0 >= P && i0 + NODES <= g.N - 2 * P;
+  // (uniform over the lanes that are here together: see factor_body_stream)
+  const unsigned am = __activemask();
+  const bool allreg = __all_sync(am, i0 >= P && i0 + NODES <= g.N - 2 * P);
   double win[NF][NODES + 2 * P];
   gs_load_windows<NODES>(win, i0, cx, g, b, sd);
   Star mine = Star::identity();
   double cur[BETA][WB], nxt[BETA][WB];
 #pragma unroll
   for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, b, 0, a, cst, allreg);
+  __syncwarp(am);      // the lane that walked special rows rejoins (else the warp stays split)
 #pragma unroll
   for (int k = 0; k < NSB; ++k) {
 #pragma unroll
     for (int r = 0; r < BETA; ++r) node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, b, 0, a, cst, allreg);
+    __syncwarp(am);
     double Dh[BETA * BETA], Z[BETA * 2 * BETA], Rr[BETA * BETA];
 #pragma unroll
     for (int r = 0; r < BETA; ++r)
@@ -583,7 +641,9 @@ __device__ __noinline__ void gs_factor_pass2(const Geom& g, const Buf& b, GsCtx&
   constexpr int NSB = C / BETA;
   const int chunk = th.chunk0 + h;
   const int i0 = chunk * M;
-  const bool allreg = i0 >= P && i0 + NODES <= g.N - 2 * P;
+  // (uniform over the lanes that are here together: see factor_body_stream)
+  const unsigned am = __activemask();
+  const bool allreg = __all_sync(am, i0 >= P && i0 + NODES <= g.N - 2 * P);
   double win[NF][NODES + 2 * P];
   gs_load_windows<NODES>(win, i0, cx, g, b, sd);
   double* Ug = b.Uf + th.cb(h) * (BETA + 1) - (long long)(th.cl + h) * BETA;   // row r, entry q: [(r*(BETA+1)+q)*32]
@@ -602,10 +662,12 @@ __device__ __noinline__ void gs_factor_pass2(const Geom& g, const Buf& b, GsCtx&
   double cur[BETA][WB], nxt[BETA][WB];
 #pragma unroll
   for (int r = 0; r < BETA; ++r) node_row<NODES>(cur[r], win, r, i0, g, b, 0, a, cst, allreg);
+  __syncwarp(am);      // the lane that walked special rows rejoins (else the warp stays split)
 #pragma unroll
   for (int k = 0; k < NSB; ++k) {
 #pragma unroll
     for (int r = 0; r < BETA; ++r) node_row<NODES>(nxt[r], win, (k + 1) * BETA + r, i0, g, b, 0, a, cst, allreg);
+    __syncwarp(am);
     double A2[2 * BETA][WB];
 #pragma unroll
     for (int r = 0; r < BETA; ++r)
@@ -671,6 +733,7 @@ __device__ __forceinline__ void gs_factor(const Geom& g, const Buf& b, GsCtx& cx
     }
   }
   GS_STAMP(1);
+  GS_STAMP_MAX(22);
   const Star pre = gs_scan<Star, false>(mine, cx, 0);
   GS_STAMP(2);
 #pragma unroll
@@ -704,13 +767,11 @@ __device__ __forceinline__ void gs_factor(const Geom& g, const Buf& b, GsCtx& cx
     if (bad) atomicOr(cx.status, bad);
   }
   // first rows of the tile: multipliers with respect to the previous tile's pivots
-  if (th.t == 0) {
-#pragma unroll
-    for (int r = 0; r < BETA; ++r)
-#pragma unroll
-      for (int q = r + 1; q <= BETA; ++q)
-        sL[gs_sl(r, q - 1, 0, 0, th.T)] =
-            (cx.tile == 0) ? 0.0 : gs_wait(cx, cx.rec.lnext(cx.tile - 1) + r * BETA + q - 1, 1);
+  if (th.t < BETA * BETA) {                 // (one word per thread: a single round trip)
+    const int r = th.t / BETA, q = th.t % BETA + 1;
+    if (q > r)
+      sL[gs_sl(r, q - 1, 0, 0, th.T)] =
+          (cx.tile == 0) ? 0.0 : gs_wait(cx, cx.rec.lnext(cx.tile - 1) + r * BETA + q - 1, 1);
   }
   __syncthreads();
   // the periodic corner block F_top was assembled with the border rows (last tile); the first
@@ -1101,13 +1162,15 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
 #pragma unroll
         for (int k = 0; k < BETA * BETA; ++k) nz = nz || (pre.PhiL()[k] != 0.0) || (pre.PhiG()[k] != 0.0);
         if (nz) {
+          double w0all[2 * NB * BETA];            // [W | G][NB][BETA]: one round trip
+          gs_wait_many<2 * NB * BETA>(cx, cx.rec.w0(), w0all, 13);
 #pragma unroll
           for (int c = 0; c < NB; ++c) {
             double vW[BETA], vG[BETA];
 #pragma unroll
             for (int t = 0; t < BETA; ++t) {
-              vW[t] = gs_wait(cx, cx.rec.w0() + c * BETA + t, 13);
-              vG[t] = gs_wait(cx, cx.rec.w0() + (NB + c) * BETA + t, 13);
+              vW[t] = w0all[c * BETA + t];
+              vG[t] = w0all[(NB + c) * BETA + t];
             }
 #pragma unroll
             for (int i = 0; i < BETA; ++i) {

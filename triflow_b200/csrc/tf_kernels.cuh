@@ -567,6 +567,8 @@ __device__ __noinline__ void assemble_special(int i, const Geom& g, const double
   // zero-then-accumulate below when they run in different warps)
   for (int k = 0; k < V * WB; ++k) rows[k] = 0.0;
   const int nint = g.N - P;                 // interior nodes
+  // The border tables live in global memory: every entry is accumulated in a local row and
+  // stored once (no read-modify-write round trips on the critical path of the end tiles).
   if (i >= nint) {                          // border or padding: identity row in the band
     for (int e = 0; e < V; ++e) rows[e * WB + BETA] = 1.0;
     if (i >= g.N || btab == nullptr) return;
@@ -574,37 +576,42 @@ __device__ __noinline__ void assemble_special(int i, const Geom& g, const double
     double* Fb = btab + 3 * NB * NB;
     double* Ab = btab + 4 * NB * NB;
     for (int e = 0; e < V; ++e) {
+      double ft[NB], fb[NB], ab[NB];
+      for (int c = 0; c < NB; ++c) { ft[c] = 0.0; fb[c] = 0.0; ab[c] = 0.0; }
+      for (int kk = 0; kk < NNZ; ++kk) {
+        if (tf_j_eq(kk) != e) continue;
+        const int var = tf_j_var(kk), off = tf_j_off(kk);
+        const int j = map_node(i + off, g);
+        if (j >= nint) ab[(j - nint) * V + var] += jv[kk];
+        else if (j < P) ft[j * V + var] += jv[kk];
+        else fb[(j - (g.N - 2 * P)) * V + var] += jv[kk];
+      }
       const int r = (i - nint) * V + e;
-      for (int c = 0; c < NB; ++c) { Ft[r * NB + c] = 0.0; Fb[r * NB + c] = 0.0; Ab[r * NB + c] = 0.0; }
-    }
-    for (int kk = 0; kk < NNZ; ++kk) {
-      const int e = tf_j_eq(kk), var = tf_j_var(kk), off = tf_j_off(kk);
-      const int r = (i - nint) * V + e;
-      const int j = map_node(i + off, g);
-      if (j >= nint) Ab[r * NB + (j - nint) * V + var] += jv[kk];
-      else if (j < P) Ft[r * NB + j * V + var] += jv[kk];
-      else Fb[r * NB + (j - (g.N - 2 * P)) * V + var] += jv[kk];
+      for (int c = 0; c < NB; ++c) { Ft[r * NB + c] = ft[c]; Fb[r * NB + c] = fb[c]; Ab[r * NB + c] = ab[c]; }
     }
     return;
   }
-  double dummy[NB * NB];
-  double* Et = btab ? btab : dummy;
-  double* Eb = btab ? btab + NB * NB : dummy;
   const bool top = i < P, bot = i >= g.N - 2 * P;
   const bool wr = btab != nullptr;
-  if (top && wr) for (int e = 0; e < V; ++e) for (int c = 0; c < NB; ++c) Et[(i * V + e) * NB + c] = 0.0;
-  if (bot && wr) for (int e = 0; e < V; ++e) for (int c = 0; c < NB; ++c)
-    Eb[((i - (g.N - 2 * P)) * V + e) * NB + c] = 0.0;
+  double eacc[V][NB];
+  for (int e = 0; e < V; ++e) for (int c = 0; c < NB; ++c) eacc[e][c] = 0.0;
   for (int kk = 0; kk < NNZ; ++kk) {
     const int e = tf_j_eq(kk), var = tf_j_var(kk), off = tf_j_off(kk);
     const int j = map_node(i + off, g);
     if (j < nint) {
       rows[e * WB + BETA + (j - i) * V + var - e] += jv[kk];
-    } else if (wr) {
-      const int c = (j - nint) * V + var;
-      if (top) Et[(i * V + e) * NB + c] += jv[kk];
-      else Eb[((i - (g.N - 2 * P)) * V + e) * NB + c] += jv[kk];
+    } else {
+      eacc[e][(j - nint) * V + var] += jv[kk];
     }
+  }
+  if (wr && (top || bot)) {
+    double* Et = btab;
+    double* Eb = btab + NB * NB;
+    for (int e = 0; e < V; ++e)
+      for (int c = 0; c < NB; ++c) {
+        if (top) Et[(i * V + e) * NB + c] = eacc[e][c];
+        if (bot) Eb[((i - (g.N - 2 * P)) * V + e) * NB + c] = eacc[e][c];
+      }
   }
   for (int e = 0; e < V; ++e)
     for (int d = 0; d < WB; ++d) {
@@ -883,7 +890,11 @@ __device__ __forceinline__ void factor_body_stream(const Geom& g, const Buf& b, 
   double win[NF][NODES + 2 * P];
   Star mine = Star::identity();
   int bad = 0;
-  const bool allreg = i0 >= P && i0 + NODES <= g.N - 2 * P;
+  // warp-uniform: in the warp that holds rows at the ends of the domain every lane takes the
+  // generic row path (nearly as fast for regular rows) -- with a per-lane choice that warp ran
+  // the whole row assembly twice, once per side of the branch (the first and the last tile are
+  // on the critical path of every scan)
+  const bool allreg = __all_sync(0xffffffffu, i0 >= P && i0 + NODES <= g.N - 2 * P);
   if (active) {
     load_windows<NODES, 0>(win, i0, g, b, sys, nullptr);
     double cur[BETA][WB], nxt[BETA][WB];
