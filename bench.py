@@ -214,8 +214,10 @@ def run_gpu(args):
 
     with ClockSampler(local) as clocks:
         clocks.wait_first()
-        for _ in range(args.warmup):
-            ens.step(dt, 1)
+        # W untimed warm-up steps in ONE call, like the timed K: a run of >= 3 steps replays a
+        # captured step graph, and building it (~0.2 ms) belongs to the warm-up, not to K steps
+        if args.warmup > 0:
+            ens.step(dt, args.warmup)
         ens.sync()
         # -- timed region: K steps, state resident in HBM
         launches0 = lib.tf_ctx_launch_count(ctx)
@@ -254,7 +256,7 @@ def run_gpu(args):
     # Per-launch figures that only a profiler can give (DRAM bytes, fp64 instruction counts)
     # are STATIC: taken from the committed ncu capture named in `static_source`, scaled by the
     # nodes of this run -- not measured in this process.
-    static, spath = {}, os.path.join(ROOT, "profiles", "r2_static.json")
+    static, spath = {}, os.path.join(ROOT, "profiles", "r2b_static.json")
     if os.path.exists(spath):
         with open(spath) as f:
             static = json.load(f)

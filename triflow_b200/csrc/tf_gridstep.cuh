@@ -169,8 +169,11 @@ struct GsRec {
   LbWord* base;          // own area
   int tiles;             // tiles per rank
   int nranks;
+  int first;             // global index of this rank's first tile
   __device__ __forceinline__ LbWord* area(int& tile) const {     // owner's area; tile -> local index
     if (!GS_MULTI || nranks == 1) return base;
+    const int lt = tile - first;
+    if ((unsigned)lt < (unsigned)tiles) { tile = lt; return base; }   // (the common case: own tile)
     const int r = tile / tiles;
     tile -= r * tiles;
     return bases[r];
@@ -421,8 +424,11 @@ __device__ __noinline__ Mon gs_lookback(const Mon& aggregate, GsCtx& cx, int ph,
 
 // ---- exclusive prefix of every thread's element over (thread, tile) order, or the mirrored
 //      order (REV: backward substitution).  Warp shuffles -> shared memory -> look-back.
+#ifndef TF_GS_SCAN_ATTR
+#define TF_GS_SCAN_ATTR __forceinline__
+#endif
 template <class Mon, bool REV>
-__device__ __forceinline__ Mon gs_scan(const Mon& mine, GsCtx& cx, int ph) {
+__device__ TF_GS_SCAN_ATTR Mon gs_scan(const Mon& mine, GsCtx& cx, int ph) {
   double* smem = cx.sh->scan;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = cx.T >> 5;
   const int ml = REV ? 31 - lane : lane;
@@ -529,8 +535,12 @@ __device__ __forceinline__ void gs_load_windows(double (&win)[NF][NODES + 2 * P]
     return;
   }
   if (lo >= cx.node_off && hi <= cx.node_off + cx.nodes_local && lo >= 0 && hi <= g.N) {
-#pragma unroll
-    for (int w = 0; w < NODES + 2 * P; ++w) win[0][w] = b.U[vidx(lo + w - cx.node_off, 0)];
+    // inside the slab, away from the ends of the domain: the pipeline's loader on slab-local
+    // indices (neighbour-lane addresses with constant offsets; a slab starts at a warp-block)
+    Geom gl = g;
+    gl.N = cx.nodes_local;
+    gl.periodic = 0;
+    load_windows<NODES, 0>(win, i0 - cx.node_off, gl, b, 0, nullptr);
     return;
   }
   // ends of the domain / of the slab: own nodes from memory, another rank's as words -- all
@@ -1521,6 +1531,7 @@ extern "C" __global__ void __launch_bounds__(tfk::GS_NT, TF_GS_MINB) TF_GS_KNAME
   cx.rec.base = (LbWord*)b.gs;
   cx.rec.tiles = (int)gridDim.x;
   cx.rec.nranks = mr.nranks;
+  cx.rec.first = (GS_MULTI ? mr.rank : 0) * (int)gridDim.x;
 #pragma unroll
   for (int r = 0; r < TF_GS_MAXRANKS; ++r) cx.rec.bases[r] = (LbWord*)mr.bases[r];
   cx.sh = &sh;
@@ -1617,6 +1628,7 @@ extern "C" __global__ void tf_k_gs_seed(tfk::Geom g, tfk::Buf b, TfGsMulti mr, i
   rec.base = (LbWord*)b.gs;
   rec.tiles = tiles_local;
   rec.nranks = 1;                                 // own area, local tile indices
+  rec.first = 0;
   const long long tag = ld_flag(b.ctl + 0);
   const int TN = T * GS_G * M;
   const int node_off = mr.rank * tiles_local * TN;

@@ -58,11 +58,6 @@ struct TfStage {
   int has_pred;
   double b[TF_MAXS];
   double bp[TF_MAXS];
-  /* Dirichlet post-hook fused into the system-resident kernel (scalar models): bit 0 left,
-     bit 1 right end of every system's U+ (reference core/schemes.py:145 hook(t, fields, pars)) */
-  int dirmask;
-  int pad_;
-  double dirv[2];
 };
 
 
@@ -87,9 +82,4 @@ struct TfStepDesc {
   double cfac[TF_MAXS][TF_MAXS];    /* gamma_ij / gamma_ii */
   double b[TF_MAXS];
   double bp[TF_MAXS];
-  /* Dirichlet post-hook fused into the system-resident kernel (scalar models): bit 0 left,
-     bit 1 right end of every system's U+ (reference core/schemes.py:145 hook(t, fields, pars)) */
-  int dirmask;
-  int pad_;
-  double dirv[2];
 };

@@ -800,11 +800,6 @@ __device__ __forceinline__ void sysstep_body(const tfk::Geom& g, const tfk::Buf&
       }
     }
     SYS_CLK(3);                                          // all stages
-    // declarative post-hook: the threads that own (and have just written) the end nodes
-    if (sd.dirmask) {
-      if ((sd.dirmask & 1) && threadIdx.x == 0) b.Un[sys * vs + vidx(0, 0)] = sd.dirv[0];
-      if ((sd.dirmask & 2) && (int)threadIdx.x == (g.N - 1) / M) b.Un[sys * vs + vidx(g.N - 1, 0)] = sd.dirv[1];
-    }
     // error estimate of the system
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (sd.has_pred) {
