@@ -216,7 +216,8 @@ int tf_ring_release(tf_ring_t ring);
  * memory over NVLink -- no collective call and no kernel boundary inside a step.  All ranks
  * must call tf_scheme_step with the same arguments; the error estimate returned is the rank's
  * own (reduce with max over ranks).  Scalar models with uniform parameters, tableaux of at
- * most 3 stages, fixed steps, no hooks.  tf_state_slab_attach_local is the single-process
+ * most 3 stages, fixed steps; tf_hook_set_dirichlet on non-periodic grids (every rank sets the
+ * same hook, the ranks that own the ends apply it).  tf_state_slab_attach_local is the single-process
  * form: the states of all ranks (rank order) live in the calling process. */
 int tf_state_create_slab(tf_ctx_t ctx, tf_model_t m, int N, int periodic, int rank, int nranks,
                          tf_state_t* out);

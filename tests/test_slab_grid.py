@@ -59,12 +59,19 @@ def _case(name, N):
     if name == "burgers":
         m = gmodel("burgers_up1")
         return m, S.ROS2(m), W.burgers(N, 1)
+    if name == "advdiff":                     # non-periodic, Dirichlet hook at both ends
+        m = gmodel("advdiff")
+        c = W.readme(N)
+        c["dt"] = 0.01
+        c["hook"] = S.Dirichlet(U=(1.0, 0.0))
+        return m, S.ROS3PRw(m, **FX), c
     raise KeyError(name)
 
 
 def _single(m, sch, c, steps):
     from triflow_b200.ensemble import Ensemble
-    ens = Ensemble(m, sch, c["x"], c["fields"], c["pars"], batch=1)
+    from triflow_b200 import schemes as S
+    ens = Ensemble(m, sch, c["x"], c["fields"], c["pars"], hook=c.get("hook", S.null_hook), batch=1)
     ens.set_fusion(False)                      # the per-kernel pipeline
     ens.step(c["dt"], steps)
     u = ens.download()[0].copy()
@@ -74,7 +81,7 @@ def _single(m, sch, c, steps):
 
 def _slab(m, sch, c, steps, devices):
     from triflow_b200.distributed import SlabGrid
-    g = SlabGrid(m, sch, c["x"], c["fields"], c["pars"], devices=devices)
+    g = SlabGrid(m, sch, c["x"], c["fields"], c["pars"], devices=devices, hook=c.get("hook"))
     g.step(c["dt"], 1)
     g.step(c["dt"], steps - 1)
     u = g.gather()
@@ -85,7 +92,7 @@ def _slab(m, sch, c, steps, devices):
 
 
 CASES = [("ks", 20000), ("ks", 50001), ("ks", 2049), ("ks_edge", 30000), ("ks_theta", 70001),
-         ("heat", 20000), ("burgers", 40000)]
+         ("heat", 20000), ("burgers", 40000), ("advdiff", 20000)]
 
 
 @pytest.mark.parametrize("name,N", CASES)
@@ -118,7 +125,7 @@ def test_slab_state_rejects_what_it_cannot_do():
     m, sch, c = _case("ks", 20000)
     g = SlabGrid(m, sch, c["x"], c["fields"], c["pars"], devices=[0])
     L, h = _lib.lib(), g.states[0].h
-    assert L.tf_hook_set_dirichlet(h, 0, 1, 0.0, 0, 0.0) == _lib.TF_EINVAL
+    assert L.tf_hook_set_dirichlet(h, 0, 1, 0.0, 0, 0.0) == _lib.TF_EINVAL      # periodic grid
     idt, nfs, le = C.c_double(), C.c_int(), C.c_double()
     assert L.tf_scheme_advance(h, sch.handle, 0.0, 0.1, 1e-2, 0.9, 100, 1e-12, 1, C.byref(idt),
                                C.byref(nfs), C.byref(le)) == _lib.TF_EINVAL

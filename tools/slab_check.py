@@ -41,11 +41,17 @@ def make(case, N):
     if case == "burgers":
         m = Model(**W.model_args("burgers_up1"), compiler="cuda")
         return m, S.ROS2(m), W.burgers(N, 1)
+    if case == "advdiff":          # non-periodic, Dirichlet hook at both ends
+        m = Model(**W.model_args("advdiff"), compiler="cuda")
+        c = W.readme(N)
+        c["dt"] = 0.01
+        c["hook"] = S.Dirichlet(U=(1.0, 0.0))
+        return m, S.ROS3PRw(m, **fx), c
     raise SystemExit(case)
 
 
 def single(m, sch, c, steps, timing):
-    e = Ensemble(m, sch, c["x"], c["fields"], c["pars"], batch=1)
+    e = Ensemble(m, sch, c["x"], c["fields"], c["pars"], hook=c.get("hook", S.null_hook), batch=1)
     e.step(c["dt"], steps)
     e.sync()
     u = e.download()[0].copy()
@@ -64,7 +70,7 @@ def single(m, sch, c, steps, timing):
 
 
 def slab(m, sch, c, steps, timing, devices):
-    g = D.SlabGrid(m, sch, c["x"], c["fields"], c["pars"], devices=devices)
+    g = D.SlabGrid(m, sch, c["x"], c["fields"], c["pars"], devices=devices, hook=c.get("hook"))
     try:
         if os.environ.get("SLAB_DEBUG"):
             g.step(c["dt"], 1)
@@ -128,7 +134,8 @@ def main():
     n = len(devices) if devices else D.world()[1]
     ok = True
     if not sizes:
-        for case, N in (("ks", 20000), ("ks", 50001), ("ks_edge", 30000), ("heat", 20000), ("burgers", 40000)):
+        for case, N in (("ks", 20000), ("ks", 50001), ("ks_edge", 30000), ("heat", 20000), ("burgers", 40000),
+                        ("advdiff", 30000)):
             ok &= check(case, N, 3, devices)
         if not (devices and len(set(devices)) < len(devices)):
             ok &= check("ks", n << 20, 3, devices, timing=20)

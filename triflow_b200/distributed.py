@@ -193,15 +193,17 @@ class SlabGrid:
     Every rank constructs it with the same arguments (``x`` and ``fields`` of the WHOLE grid);
     rank ``r`` keeps nodes ``node_off .. node_off + n_local - 1`` on its GPU.  ``step`` launches the same cooperative step kernel on every GPU;
     inside a step the GPUs are coupled only through tagged words read from the neighbour's
-    memory over NVLink.  Fixed steps, scalar model, uniform parameters, tableaux of <= 3 stages.
+    memory over NVLink.  Fixed steps, scalar model, uniform parameters, tableaux of <= 3 stages;
+    ``hook``: ``schemes.Dirichlet`` on non-periodic grids.
 
     ``devices``: single-process form -- one Python process drives the listed GPUs (the object
     then holds the slabs of all ranks and ``upload`` / ``download`` take the whole grid).
     """
 
-    def __init__(self, model, scheme, x, fields, pars, devices=None):
+    def __init__(self, model, scheme, x, fields, pars, devices=None, hook=None):
         from . import _lib
         from .compiler import CompiledModel
+        from .schemes import Dirichlet
         self.model, self.scheme = model, scheme
         x = np.asarray(x, dtype=np.float64)
         self.N = x.size
@@ -239,6 +241,13 @@ class SlabGrid:
         for s in self.states:
             table = s.variant.lowered.uniform_table(dx, pars, 1)
             s.upload(consts=table)
+            if isinstance(hook, Dirichlet):            # declarative hook, non-periodic grids
+                left, right = hook.values[var]
+                _lib.check(_lib.lib().tf_hook_set_dirichlet(
+                    s.h, 0, left is not None, 0.0 if left is None else float(left),
+                    right is not None, 0.0 if right is None else float(right)))
+            elif hook is not None and getattr(hook, "__name__", "") != "null_hook":
+                raise ValueError("slab grids take declarative hooks (schemes.Dirichlet) only")
         self.upload(u)
 
     # -- this rank's part of the grid
