@@ -294,17 +294,25 @@ def run_gpu(args):
     if args.workload == "ensemble" and ws > 1:
         # the first collective of a process group builds the NCCL communicator (hundreds of
         # ms): not part of the gather
-        D.gather_members(np.zeros((batch, 1)), args.members)
+        import torch
+        D.gather_members(torch.zeros((batch, 1), dtype=torch.float64, device="cuda"), args.members)
+        h_full = _lib.pinned_empty((args.members, N * model._nvar)) if rank == 0 else None
     D.barrier()
     t0 = time.perf_counter()
-    u_local = ens.download(out=h_final)
-    gathered = D.gather_members(u_local, args.members) if args.workload == "ensemble" else u_local
+    if args.workload == "ensemble" and ws > 1:
+        # sharded ensemble: unpack on the device, NCCL gather over NVLink, one copy to the host
+        gathered = D.gather_members(ens.download_to_torch(), args.members, out=h_full)
+    else:
+        gathered = ens.download(out=h_final)
     t_gather = D.max_over_ranks(time.perf_counter() - t0)
     final_gather = {"ms": t_gather * 1e3, "bytes": int(8 * total_units * model._nvar),
-                    "what": "device -> host download on every rank + gather to rank 0",
+                    "what": ("unpack on the device, NCCL gather to rank 0, one device -> pinned host copy there"
+                             if ws > 1 else "device -> host download"),
                     "value_incl_gather": total_units * args.steps / (t_max + t_gather)}
     if rank == 0 and args.workload == "ensemble":
         assert gathered.shape[0] == args.members
+        if ws > 1:                                # this rank's block arrived where it belongs
+            assert np.array_equal(gathered[lo:hi], ens.download(out=h_final)), "gather misplaced a block"
     del gathered
 
     # -- end to end through the public API with HOST buffers: every step uploads the

@@ -96,6 +96,9 @@ int tf_state_upload(tf_state_t st, const double* x, const double* u, const doubl
                     const double* nodepars, const double* consts);
 /* u [batch][n_nodes*nvar]: inverse of upload, BaseFields.fill order (core/fields.py:173-183) */
 int tf_state_download(tf_state_t st, double* u);
+/* same layout written to DEVICE memory (dev_u: batch*n_nodes*nvar doubles on the state's GPU),
+ * e.g. the send buffer of the final gather of a sharded ensemble: no host round trip */
+int tf_state_download_device(tf_state_t st, double* dev_u);
 
 /* F_Routine.__call__ -> compute_F_numpy (core/routines.py:37-45, compilers.py:281-289):
  * out [batch][n_nodes*nvar]. */

@@ -127,6 +127,7 @@ def lib():
         "tf_model_read_symbol": [vp, C.c_char_p, vp, C.c_size_t],
         "tf_state_create": [vp, vp, i, i, i, C.POINTER(vp)], "tf_state_destroy": [vp],
         "tf_state_upload": [vp, dp, dp, dp, dp, dp], "tf_state_download": [vp, dp],
+        "tf_state_download_device": [vp, vp],
         "tf_eval_F": [vp, dp], "tf_eval_J": [vp, dp],
         "tf_scheme_create": [vp, i, dp, dp, dp, dp, C.POINTER(vp)],
         "tf_scheme_destroy": [vp],
@@ -160,7 +161,7 @@ EXPORTS = ["tf_last_error", "tf_ctx_create", "tf_ctx_destroy", "tf_ctx_sync", "t
            "tf_host_alloc", "tf_host_alloc_wc", "tf_ctx_fp64_peak", "tf_ring_create",
            "tf_ring_destroy", "tf_ring_push", "tf_ring_pop", "tf_ring_release",
            "tf_host_free", "tf_model_load", "tf_model_unload", "tf_model_read_symbol", "tf_state_create",
-           "tf_state_destroy", "tf_state_upload", "tf_state_download", "tf_eval_F",
+           "tf_state_destroy", "tf_state_upload", "tf_state_download", "tf_state_download_device", "tf_eval_F",
            "tf_eval_J", "tf_scheme_create", "tf_scheme_destroy", "tf_hook_set_dirichlet",
            "tf_hook_clear", "tf_scheme_step", "tf_scheme_advance", "tf_state_status",
            "tf_state_set_factor_reuse", "tf_state_set_fusion", "tf_ensemble_advance",

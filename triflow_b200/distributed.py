@@ -77,24 +77,41 @@ def sum_over_ranks(value):
     return float(t.item())
 
 
-def gather_members(local, n_members):
-    """Final gather of per-member rows ``local`` (n_local, width) to rank 0 in
-    member order.  Returns the full array on rank 0, ``None`` elsewhere."""
+def gather_members(local, n_members, out=None):
+    """Final gather of per-member rows ``local`` (n_local, width) to rank 0 in member order.
+    ``out``: optional ``(n_members, width)`` numpy array on rank 0 for the result (page-locked,
+    ``_lib.pinned_empty``, for a full-speed copy).
+    ``local``: a numpy array, or -- NCCL backend -- a ``torch`` CUDA tensor
+    (``Ensemble.download_to_torch``): then nothing crosses PCIe except rank 0's single copy of
+    the result to the host.  Returns the full array on rank 0, ``None`` elsewhere."""
     import torch
     import torch.distributed as dist
+    out_host = out
+    on_device = isinstance(local, torch.Tensor)
     if not (dist.is_available() and dist.is_initialized()):
-        return np.asarray(local)
+        return local.cpu().numpy() if on_device else np.asarray(local)
     rank, ws = dist.get_rank(), dist.get_world_size()
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
     width = local.shape[1]
     sizes = [shard(n_members, r, ws) for r in range(ws)]
     nmax = max(hi - lo for lo, hi in sizes)
-    buf = torch.zeros((nmax, width), dtype=torch.float64, device=dev)
-    buf[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+    if on_device and local.shape[0] == nmax and dev == "cuda":
+        buf = local                                  # equal shards: send the state buffer itself
+    else:
+        buf = torch.zeros((nmax, width), dtype=torch.float64, device=dev)
+        src = local if on_device else torch.from_numpy(np.ascontiguousarray(local))
+        buf[: local.shape[0]] = src.to(dev)
     out = [torch.empty_like(buf) for _ in range(ws)] if rank == 0 else None
     dist.gather(buf, out, dst=0)
     if rank != 0:
         return None
+    if dev == "cuda":                                # one device -> host copy of the result
+        res = np.empty((n_members, width)) if out_host is None else out_host
+        full = torch.from_numpy(res)
+        for o, (lo, hi) in zip(out, sizes):
+            full[lo:hi].copy_(o[: hi - lo])
+        torch.cuda.synchronize()
+        return res
     return np.concatenate([o[: hi - lo].cpu().numpy() for o, (lo, hi) in zip(out, sizes)])
 
 

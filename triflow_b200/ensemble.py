@@ -143,6 +143,17 @@ class Ensemble:
     def download(self, out=None):
         return self.state.download(out)
 
+    def download_to_torch(self):
+        """The states as a ``torch`` CUDA tensor ``(batch, N*nvar)`` on this rank's GPU (no host
+        copy): the send buffer of :func:`triflow_b200.distributed.gather_members`."""
+        import ctypes as C
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        out = torch.empty((self.batch, self.N * self.nvar), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().tf_state_download_device(self.state.h, C.c_void_p(out.data_ptr())))
+        _lib.check(_lib.lib().tf_ctx_sync(self.state.ctx))
+        return out
+
     def member_fields(self, r, u=None):
         u = self.download() if u is None else u
         cols = u[r].reshape(self.N, self.nvar)
