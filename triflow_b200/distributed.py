@@ -228,6 +228,7 @@ class SlabGrid:
         (var,) = model._dep_vars
         u = np.asarray(fields[var], dtype=np.float64)
         self.t = 0.0
+        self._deferred = None
         self._local = devices is not None
         dx = (x[-1] - x[0]) / (x.size - 1)                       # compilers.py:234-237
         if self._local:
@@ -247,14 +248,30 @@ class SlabGrid:
         else:
             import torch.distributed as dist
             self.rank, self.nranks = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
-            st = _SlabState(model._cuda, self.N, periodic, self.rank, self.nranks)
-            self.states = [st]
+            # every step below is collective: a failure on one rank must fail all of them, or the
+            # others would wait for it in the next collective / spin on its words
+            err, st = None, None
+            try:
+                st = _SlabState(model._cuda, self.N, periodic, self.rank, self.nranks)
+                handle = st.export()
+            except Exception as e:  # noqa: BLE001
+                err, handle = e, b""
+            self.states = [st] if st is not None else []
             handles = [None] * self.nranks
             if self.nranks > 1:
-                dist.all_gather_object(handles, st.export())
+                dist.all_gather_object(handles, handle)
             else:
-                handles = [st.export()]
-            st.attach(handles)
+                handles = [handle]
+            if err is None and all(len(h) == 64 for h in handles):
+                try:
+                    st.attach(handles)
+                except Exception as e:  # noqa: BLE001
+                    err = e
+            elif err is None:
+                err = RuntimeError("slab grid: another rank could not create its slab")
+            if max_over_ranks(0.0 if err is None else 1.0) > 0:
+                self.close()
+                raise err if err is not None else RuntimeError("slab grid: another rank failed to attach")
         for s in self.states:
             table = s.variant.lowered.uniform_table(dx, pars, 1)
             s.upload(consts=table)
@@ -291,18 +308,32 @@ class SlabGrid:
         from . import _lib
         L = _lib.lib()
         for s in self.states:
-            _lib.check(L.tf_scheme_step(s.h, self.scheme.handle, float(dt), int(n_steps), None))
+            try:
+                _lib.check(L.tf_scheme_step(s.h, self.scheme.handle, float(dt), int(n_steps), None))
+            except Exception as e:  # noqa: BLE001  (reported by the next sync(), on every rank)
+                self._deferred = self._deferred or ("rank %d: %s" % (s.rank, e))
         self.t += n_steps * dt
 
     def sync(self):
+        """Wait for the steps issued so far.  Collective in the one-process-per-GPU form: every
+        rank learns whether ANY rank failed (a time-out on one rank is every rank's error)."""
         from . import _lib
+        bad, self._deferred = self._deferred, None
         for s in self.states:
-            _lib.check(_lib.lib().tf_ctx_sync(s.ctx))
-        for s in self.states:
-            st = s.status()
-            if st:
-                raise RuntimeError("slab grid: rank %d reports status %d (bit 2: a tile timed out "
-                                   "waiting for a neighbour; bits 0/1/3: factorisation)" % (s.rank, st))
+            try:
+                _lib.check(_lib.lib().tf_ctx_sync(s.ctx))
+                st = s.status()
+            except Exception as e:  # noqa: BLE001
+                bad = bad or ("rank %d: %s" % (s.rank, e))
+                continue
+            if st and bad is None:
+                bad = ("rank %d reports status %d (bit 2: a tile timed out waiting for a "
+                       "neighbour; bits 0/1/3: factorisation)" % (s.rank, st))
+        anybad = bad is not None
+        if not self._local and self.nranks > 1:
+            anybad = max_over_ranks(1.0 if anybad else 0.0) > 0
+        if anybad:
+            raise RuntimeError("slab grid: " + (bad or "another rank failed"))
 
     def download(self):
         """This rank's nodes (single-process form: the whole grid)."""
