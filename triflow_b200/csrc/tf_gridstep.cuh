@@ -494,29 +494,35 @@ __device__ __forceinline__ int gs_ss(int r, int h, int t, int T) { return (r * G
 
 // stage state of node j (any tile) from global memory: U + ((alpha_0 k_0 + ...)).  Valid for
 // nodes of the own tile (same-CTA writes, ordered by a barrier) and, at stage 0, for any node.
-template <int I>
-__device__ __forceinline__ double gs_state_global(const GsCtx& cx, const Buf& b, int j, const TfStepDesc& sd) {
+// (IT >= 0: stage index at compile time; IT < 0: run-time index irt, at most GS_STAGES - 1 terms)
+template <int IT>
+__device__ __forceinline__ double gs_state_global(const GsCtx& cx, const Buf& b, int j, const TfStepDesc& sd,
+                                                  int irt = 0) {
+  constexpr int QMAX = IT < 0 ? GS_STAGES - 1 : IT;
+  const int I = IT < 0 ? irt : IT;
   const long long a = vidx(GS_MULTI ? j - cx.node_off : j, 0);
   double u = b.U[a];
-  if (I > 0) {
+  if (QMAX > 0) {
     double acc = 0.0;
 #pragma unroll
-    for (int q = 0; q < I; ++q) {
-      const double term = __dmul_rn(sd.alpha[I][q], b.K[q][a]);
-      acc = (q == 0) ? term : __dadd_rn(acc, term);
-    }
-    u = __dadd_rn(u, acc);
+    for (int q = 0; q < QMAX; ++q)
+      if (q < I) {
+        const double term = __dmul_rn(sd.alpha[I][q], b.K[q][a]);
+        acc = (q == 0) ? term : __dadd_rn(acc, term);
+      }
+    if (I > 0) u = __dadd_rn(u, acc);
   }
   return u;
 }
 // stage state of node jm (already wrapped / clamped into [0, N)) wherever it lives
-template <int I>
+template <int IT>
 __device__ __noinline__ double gs_node_value(GsCtx& cx, const Geom& g, const Buf& b, int jm,
-                                             const TfStepDesc& sd) {
+                                             const TfStepDesc& sd, int irt = 0) {
+  const int I = IT < 0 ? irt : IT;
   const int TN = cx.T * GS_G * M;
   const int ot = jm / TN;
   const bool mine = !GS_MULTI || (jm >= cx.node_off && jm < cx.node_off + cx.nodes_local);
-  if (ot == cx.tile || (I == 0 && mine)) return gs_state_global<I>(cx, b, jm, sd);
+  if (ot == cx.tile || (I == 0 && mine)) return gs_state_global<IT>(cx, b, jm, sd, irt);
   const int loc = jm - ot * TN;
   if (loc < (I == 0 ? GS_HW : P)) return gs_wait(cx, cx.rec.halo(I, ot, 0) + loc, 10);
   if (loc >= TN - P) return gs_wait(cx, cx.rec.halo(I, ot, 1) + (loc - (TN - P)), 11);
@@ -980,11 +986,17 @@ __device__ __noinline__ void gs_border_finish(const Geom& g, const Buf& b, GsCtx
 // ------------------------------------------------------------------ one stage
 // th_alive / tile_alive: this thread's / this tile's rows of W and G may be non-zero (set by
 // stage 0, used by every stage)
-template <int I, bool LAST>
+// IT >= 0 / LT: stage index and "last stage" at compile time.  IT < 0 (-DTF_GS_RTSTAGE): ONE
+// body for the stages behind the first, index irt and lastrt at run time -- a third less code
+// per step for a kernel whose instruction fetches stall it.
+template <int IT, bool LT>
 __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx, const GsThread& th,
                                          const TfStepDesc& sd, double a, const double* sL, double* sS,
                                          const double (&phiG)[GS_G][BETA * BETA], bool& th_alive,
-                                         bool& tile_alive, double& emax) {
+                                         bool& tile_alive, double& emax, int irt = 0, bool lastrt = false) {
+  constexpr int QMAX = IT < 0 ? GS_STAGES - 1 : IT;      // bound of the loops over previous stages
+  const int I = IT < 0 ? irt : IT;
+  const bool LAST = IT < 0 ? lastrt : LT;
   GsShared& sh = *cx.sh;
   const int T = cx.T;
   const int TN = T * GS_G * M;
@@ -1006,14 +1018,15 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
         for (int r = 0; r < C; ++r) {
           const long long aidx = th.cb(h) + (long long)r * 32;
           double u = b.U[aidx];
-          if (I > 0) {
+          if (QMAX > 0) {
             double acc = 0.0;
 #pragma unroll
-            for (int q = 0; q < I; ++q) {
-              const double term = __dmul_rn(sd.alpha[I][q], b.K[q][aidx]);
-              acc = (q == 0) ? term : __dadd_rn(acc, term);
-            }
-            u = __dadd_rn(u, acc);
+            for (int q = 0; q < QMAX; ++q)
+              if (q < I) {
+                const double term = __dmul_rn(sd.alpha[I][q], b.K[q][aidx]);
+                acc = (q == 0) ? term : __dadd_rn(acc, term);
+              }
+            if (I > 0) u = __dadd_rn(u, acc);
           }
           own[h][r] = u;
         }
@@ -1032,7 +1045,7 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
 #pragma unroll
           for (int m = 0; m < M; ++m) {
             const int j = i0 + m;
-            if (j >= g.N && j < g.N + P) own[h][m] = gs_node_value<I>(cx, g, b, map_node(j, g), sd);
+            if (j >= g.N && j < g.N + P) own[h][m] = gs_node_value<IT>(cx, g, b, map_node(j, g), sd, irt);
           }
         }
       }
@@ -1048,10 +1061,10 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
       const int side = threadIdx.x / P, k = threadIdx.x - side * P;
       const int j = side == 0 ? cx.tile * TN - P + k : (cx.tile + 1) * TN + k;
       // (right of a tile that ends in padding: no real node reads it, nobody publishes it)
-      sh.halo[side][k] = (j < g.N + P) ? gs_node_value<I>(cx, g, b, map_node(j, g), sd) : 0.0;
+      sh.halo[side][k] = (j < g.N + P) ? gs_node_value<IT>(cx, g, b, map_node(j, g), sd, irt) : 0.0;
     }
     // the first chunk of a periodic system starts the recurrences of W and G: F_top
-    if (I == 0 && g.periodic && cx.tiles > 1 && cx.tile == 0 && threadIdx.x >= 2 * P &&
+    if (IT == 0 && g.periodic && cx.tiles > 1 && cx.tile == 0 && threadIdx.x >= 2 * P &&
         threadIdx.x < 2 * P + NB * NB)
       sh.ftop[threadIdx.x - 2 * P] = gs_wait(cx, cx.rec.ftop() + (threadIdx.x - 2 * P), 5);
     __syncthreads();
@@ -1093,7 +1106,8 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
           }
           double rhs = __dmul_rn(sd.dt, fe[0]);
 #pragma unroll
-          for (int q = 0; q < I; ++q) rhs = __fma_rn(sd.cfac[I][q], b.K[q][th.cb(h) + (long long)m * 32], rhs);
+          for (int q = 0; q < QMAX; ++q)
+            if (q < I) rhs = __fma_rn(sd.cfac[I][q], b.K[q][th.cb(h) + (long long)m * 32], rhs);
           rhs = (i < g.N) ? rhs : 0.0;
           rhs_all[h][m] = rhs;
           double coef[BETA];
@@ -1112,7 +1126,7 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
 #pragma unroll
       for (int t = 0; t < BETA; ++t) { ws[c][t] = 0.0; pg[c][t] = 0.0; }
     const bool first_chunk = (cx.tile == 0 && th.t == 0);
-    if (I == 0 && g.periodic) {
+    if (IT == 0 && g.periodic) {
       AffB mb[GS_G];
 #pragma unroll
       for (int h = 0; h < GS_G; ++h) {
@@ -1220,7 +1234,7 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
         }
     }
     // ------------------------------------------------------------ border fill (once per step)
-    if (I == 0) {
+    if (IT == 0) {
       th_alive = false;
       if (g.periodic && th.active) {
         th_alive = first_chunk;
@@ -1419,24 +1433,26 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
         sv[0] = v;
         const long long aidx = th.cb(h) + (long long)r * 32;
         double k = v;
-        double kprev[I > 0 ? I : 1];
+        double kprev[QMAX > 0 ? QMAX : 1];
 #pragma unroll
-        for (int q = 0; q < I; ++q) {
-          kprev[q] = b.K[q][aidx];
-          k = __fma_rn(-sd.cfac[I][q], kprev[q], k);
-        }
+        for (int q = 0; q < QMAX; ++q)
+          if (q < I) {
+            kprev[q] = b.K[q][aidx];
+            k = __fma_rn(-sd.cfac[I][q], kprev[q], k);
+          }
         if (!LAST) {
           b.K[I][aidx] = k;
         } else {
           double acc = 0.0, accp = 0.0;
 #pragma unroll
-          for (int q = 0; q <= I; ++q) {
-            const double kq = (q < I) ? kprev[q < I ? q : 0] : k;
-            const double t = __dmul_rn(sd.b[q], kq);
-            acc = (q == 0) ? t : __dadd_rn(acc, t);
-            const double tp = __dmul_rn(sd.bp[q], kq);
-            accp = (q == 0) ? tp : __dadd_rn(accp, tp);
-          }
+          for (int q = 0; q <= QMAX; ++q)
+            if (q <= I) {
+              const double kq = (q < I) ? kprev[q < QMAX ? q : 0] : k;
+              const double t = __dmul_rn(sd.b[q], kq);
+              acc = (q == 0) ? t : __dadd_rn(acc, t);
+              const double tp = __dmul_rn(sd.bp[q], kq);
+              accp = (q == 0) ? tp : __dadd_rn(accp, tp);
+            }
           const double un = __dadd_rn(b.U[aidx], acc);
           b.Un[aidx] = un;
           if (sd.has_pred) {
@@ -1465,10 +1481,11 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
             const long long aidx = th.cb(h) + (long long)r * 32;
             double acc = 0.0;
 #pragma unroll
-            for (int q = 0; q <= I; ++q) {
-              const double term = __dmul_rn(sd.alpha[I + 1][q], b.K[q][aidx]);
-              acc = (q == 0) ? term : __dadd_rn(acc, term);
-            }
+            for (int q = 0; q <= QMAX; ++q)
+              if (q <= I) {
+                const double term = __dmul_rn(sd.alpha[I + 1][q], b.K[q][aidx]);
+                acc = (q == 0) ? term : __dadd_rn(acc, term);
+              }
             const double nv = __dadd_rn(b.U[aidx], acc);
             if (e0) gs_post(cx, cx.rec.halo(I + 1, cx.tile, 0) + loc, nv);
             if (e1) gs_post(cx, cx.rec.halo(I + 1, cx.tile, 1) + (loc - (TN - P)), nv);
@@ -1574,6 +1591,16 @@ extern "C" __global__ void __launch_bounds__(tfk::GS_NT, TF_GS_MINB) TF_GS_KNAME
   gs_factor(g, b, cx, th, sd, a, sL, phiG);
   if (cx.tile == cx.tiles - 1) gs_border_bottom(g, b, cx, a, sL);
   bool th_alive = false, tile_alive = false;
+#ifdef TF_GS_RTSTAGE
+  if (sd.s == 1) {
+    gs_stage<0, true>(g, b, cx, th, sd, a, sL, sS, phiG, th_alive, tile_alive, emax);
+  } else {
+    gs_stage<0, false>(g, b, cx, th, sd, a, sL, sS, phiG, th_alive, tile_alive, emax);
+#pragma unroll 1
+    for (int i = 1; i < sd.s; ++i)
+      gs_stage<-1, false>(g, b, cx, th, sd, a, sL, sS, phiG, th_alive, tile_alive, emax, i, i == sd.s - 1);
+  }
+#else
   switch (sd.s) {
     case 1:
       gs_stage<0, true>(g, b, cx, th, sd, a, sL, sS, phiG, th_alive, tile_alive, emax);
@@ -1588,6 +1615,7 @@ extern "C" __global__ void __launch_bounds__(tfk::GS_NT, TF_GS_MINB) TF_GS_KNAME
       gs_stage<2, true>(g, b, cx, th, sd, a, sL, sS, phiG, th_alive, tile_alive, emax);
       break;
   }
+#endif
   }
   // error estimate: per-tile maximum, reduced by the last CTA to finish
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
