@@ -392,7 +392,7 @@ def test_error_paths():
     with pytest.raises(ValueError):
         S.ROS2(m)(0.0, f, 0.1, dict(periodic=True))
     with pytest.raises(ValueError):
-        S.Theta(m, solver=lambda A, b: b)
+        S.Theta(m, theta=0)                        # explicit Euler: nothing to solve on the device
     # singular system: dt huge with a sign making I - gamma*dt*J singular is model dependent;
     # NaN input must surface as an error, not as silent garbage
     x = np.linspace(0, 1, 300)

@@ -110,3 +110,67 @@ def test_reference_schemes_on_the_cuda_compiler():
         t, f = sch(t, f, c["dt"], c["pars"], hook=W.readme_hook)
         snaps.append(f.uflat.copy())
     assert np.array_equal(np.array(snaps), g["readme_fixed_ROS3PRw"])
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_interpolated_output_mode_equals_the_reference():
+    """recompute_target=False (schemes.py:183-187,217-222): the embedded controller overshoots
+    the output time and the output is interpolated between the last two internal states, the
+    interpolant serving later output times too.  Reference (numpy compiler + SuperLU) against
+    this package's ROS3PRw on the README problem, same hook, five outputs."""
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.model import Model
+    mods = ref_loader.load_reference()
+    c = W.readme(200)
+    rm = ref_model("advdiff", "numpy")
+    rs = mods["schemes"].ROS3PRw(rm, tol=1e-1, recompute_target=False)
+    gm = Model(**W.model_args("advdiff"), compiler="cuda")
+    gs = S.ROS3PRw(gm, tol=1e-1, recompute_target=False)
+    rf = rm.fields_template(x=c["x"], **c["fields"])
+    gf = gm.fields_template(x=c["x"], **c["fields"])
+    tr = tg = 0.0
+    for _ in range(5):
+        tr, rf = rs(tr, rf, c["dt"], c["pars"], hook=W.readme_hook)
+        tg, gf = gs(tg, gf, c["dt"], c["pars"], hook=W.readme_hook)
+        assert tr == tg
+        assert rel_traj_err(gf.uflat, rf.uflat) <= 1e-8
+        assert abs(gs._internal_dt - rs._internal_dt) <= 1e-9 * abs(rs._internal_dt)
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_theta_with_a_user_solver_equals_the_reference():
+    """Theta(model, theta, solver=callable) (schemes.py:518-521,548-559): the user's solver is
+    called on the host with the same A and b as in the reference (F, J from the device)."""
+    import scipy.sparse.linalg as spl
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.model import Model
+    mods = ref_loader.load_reference()
+    calls = []
+
+    def solver(A, b):
+        calls.append(A.shape)
+        return spl.spsolve(A, b)
+    c = W.readme(200)
+    rm = ref_model("advdiff", "numpy")
+    gm = Model(**W.model_args("advdiff"), compiler="cuda")
+    for theta in (1, 0.5, 0):
+        rs = mods["schemes"].Theta(rm, theta=theta, solver=solver)
+        gs = S.Theta(gm, theta=theta, solver=solver)
+        rf = rm.fields_template(x=c["x"], **c["fields"])
+        gf = gm.fields_template(x=c["x"], **c["fields"])
+        tr = tg = 0.0
+        for _ in range(3):
+            tr, rf = rs(tr, rf, 1e-3, c["pars"], hook=W.readme_hook)
+            tg, gf = gs(tg, gf, 1e-3, c["pars"], hook=W.readme_hook)
+        assert np.array_equal(gf.uflat, rf.uflat)          # bit-identical F, J -> same A, b
+    assert len(calls) == 18 and calls[0] == (200, 200)
+    # without a solver the device banded solver does the same step
+    gd = S.Theta(gm, theta=0.5)
+    gf = gm.fields_template(x=c["x"], **c["fields"])
+    rf = rm.fields_template(x=c["x"], **c["fields"])
+    rs = mods["schemes"].Theta(rm, theta=0.5)
+    tg, gf = gd(0.0, gf, 1e-3, c["pars"], hook=W.readme_hook)
+    tr, rf = rs(0.0, rf, 1e-3, c["pars"], hook=W.readme_hook)
+    assert rel_traj_err(gf.uflat, rf.uflat) <= 1e-8

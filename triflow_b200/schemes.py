@@ -269,6 +269,7 @@ class ROW_general(_DeviceScheme):
         self._max_iter = max_iter
         self._dt_min = dt_min
         self._recompute_target = recompute_target
+        self._interp_cache = None
         self._err = None
         self.n_fixed_steps = 0
 
@@ -294,10 +295,7 @@ class ROW_general(_DeviceScheme):
         return t, fields
 
     def _variable_step(self, t, fields, dt, pars, hook):
-        if not self._recompute_target:
-            raise NotImplementedError(
-                "recompute_target=False (interpolated output) is not implemented")
-        if self._on_device(hook):
+        if self._recompute_target and self._on_device(hook):
             st = self._bind(fields, pars)
             self._set_hook(st, hook)
             idt = C.c_double(-1.0 if self._internal_dt is None else self._internal_dt)
@@ -312,12 +310,22 @@ class ROW_general(_DeviceScheme):
             _lib.check(rc)
             self._err = err.value
             return t + dt, self._result(fields, st)
-        # arbitrary Python hook: the controller of schemes.py:176-238 on the host,
-        # every _fixed_step on the device.
+        # arbitrary Python hook, or recompute_target=False (output interpolated between the
+        # internal steps, schemes.py:183-187,217-222): the controller of schemes.py:176-238 on
+        # the host, every _fixed_step on the device.
         next_t = t + dt
         self._internal_iter = 0
-        dt = self._internal_dt = min(1e-6 if self._internal_dt is None
-                                     else self._internal_dt, dt)
+        if not self._recompute_target:
+            try:                                      # target inside the last internal step?
+                fields = fields.copy()
+                fields.fill(np.asarray(self._interp_cache(next_t)).ravel())
+                return next_t, fields
+            except (TypeError, ValueError):           # no cache yet / target beyond it
+                pass
+            dt = self._internal_dt = 1e-6 if self._internal_dt is None else self._internal_dt
+        else:
+            dt = self._internal_dt = min(1e-6 if self._internal_dt is None
+                                         else self._internal_dt, dt)
         while True:
             self._err = None
             while self._err is None or self._err > self._tol:
@@ -327,9 +335,16 @@ class ROW_general(_DeviceScheme):
                 dt = self._internal_dt = (self._safety_factor * dt
                                           * np.sqrt(self._tol / self._err))
             if new_t >= next_t:
-                t, fields, self._err, _ = self._fixed_step_host_hook(
-                    t, fields, next_t - t, pars, hook)
-                self.n_fixed_steps += 1
+                if self._recompute_target:
+                    t, fields, self._err, _ = self._fixed_step_host_hook(
+                        t, fields, next_t - t, pars, hook)
+                    self.n_fixed_steps += 1
+                else:
+                    from scipy.interpolate import interp1d
+                    self._interp_cache = interp1d([t, new_t], [fields.uflat[None],
+                                                               new_fields.uflat[None]], axis=0)
+                    fields = fields.copy()
+                    fields.fill(np.asarray(self._interp_cache(next_t)).ravel())
                 self._internal_iter += 1
                 fields, pars = hook(t, fields, pars)
                 return next_t, fields
@@ -384,20 +399,33 @@ class RODASPR(_Embedded):
 
 class Theta(_DeviceScheme):
     """Theta scheme (``schemes.py:502-559``): theta=1 backward Euler, 0.5
-    Crank-Nicolson.  The pluggable ``solver(A, b)`` of the reference is replaced by
-    the device banded solver and cannot be overridden."""
+    Crank-Nicolson.  By default the solve is the device banded solver; a ``solver(A, b)``
+    given by the user is called on the host like the reference does (F and J still come from
+    the device)."""
 
     def __init__(self, model, theta=1, solver=None, lazy=False):
-        if solver is not None:
-            raise ValueError("triflow_b200.Theta solves on the device; a custom "
-                             "solver(A, b) cannot be plugged in")
-        if theta == 0:
+        if theta == 0 and solver is None:
             raise ValueError("theta=0 (explicit Euler) has no implicit system to solve")
         self._theta = theta
+        self._solver = solver
         super().__init__(model, np.zeros((1, 1)), np.array([[float(theta)]]), [1.0], None)
         self.lazy = lazy
 
     def __call__(self, t, fields, dt, pars, hook=null_hook):
+        if self._solver is not None:
+            # a user-supplied solver(A, b) (schemes.py:518-521): the reference's own sequence
+            # (:548-559) with F and J evaluated on the device, A handed over as scipy CSC
+            import scipy.sparse as sps
+            fields = fields.copy()
+            fields, pars = hook(t, fields, pars)
+            F = self._model.F(fields, pars)
+            J = self._model.J(fields, pars)
+            U = fields.uflat
+            B = dt * (F - self._theta * J @ U) + U
+            A = sps.identity(U.size, format="csc") - self._theta * dt * J
+            fields.fill(self._solver(A, B))
+            fields, _ = hook(t + dt, fields, pars)
+            return t + dt, fields
         if self._on_device(hook):
             st = self._bind(fields, pars)
             self._set_hook(st, hook)
