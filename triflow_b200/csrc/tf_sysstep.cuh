@@ -319,8 +319,6 @@ __device__ __forceinline__ void sys_factor(const Geom& g, const Buf& lb, int sys
 
 // ---- one Rosenbrock stage: forward substitution of dt*F(U_i) + sum cfac_j k_j, border
 //      solve, backward substitution; k_i -> shared memory, or (last stage) U+ -> HBM.
-// ---- one Rosenbrock stage: forward substitution of dt*F(U_i) + sum cfac_j k_j, border
-//      solve, backward substitution; k_i -> shared memory, or (last stage) U+ -> HBM.
 template <int I, bool LAST>
 __device__ __forceinline__ void sys_stage(const Geom& g, const Buf& b, const Buf& lb, int sys,
                                           const TfStepDesc& sd, double dt, const double* cst,
