@@ -360,5 +360,16 @@ class SlabGrid:
         return slab_partition(self.N, self.nranks, tile_nodes, s.tiles_local)
 
     def close(self):
+        """Collective in the one-process-per-GPU form: nobody frees a record area that a peer's
+        kernel may still be reading."""
+        if not self._local and self.nranks > 1:
+            try:
+                for s in self.states:
+                    from . import _lib
+                    _lib.lib().tf_ctx_sync(s.ctx)
+                barrier()
+            except Exception:  # noqa: BLE001
+                pass
         for s in self.states:
             s.close()
+        self.states = []
