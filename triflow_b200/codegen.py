@@ -315,10 +315,42 @@ def lower(model, node_pars=()):
     out.stats = stats
     out.jacobian_is_constant = (stats["J"]["ops"] == 0 and not node_pars and
                                 all("in." not in ln for ln in bodies["J"]))
+    out.f_is_linear = bool(out.jacobian_is_constant and not model._help_funcs and not uses_x and
+                           _f_equals_j_times_u(model, fields, nvar, p, out.j_eq, out.j_var, out.j_off))
     out.fields = fields
     out.header = _render_header(out, bodies)
     out.key = hashlib.sha1(out.header.encode()).hexdigest()[:16]
     return out
+
+
+def _f_equals_j_times_u(model, fields, nvar, p, j_eq, j_var, j_off):
+    """True when every equation is homogeneous linear in the stencil values, F_e = sum_k J_k u_k
+    identically (checked symbolically): the solver kernels may then evaluate F as that sum -- a
+    few fused multiply-adds with the uniform Jacobian constants instead of the reference's
+    expanded expression (same value up to rounding; `model.F` keeps the reference's form)."""
+    import sympy as sp
+    F = model.F_array.tolist()
+    J = model._J_sparse_array.tolist()
+    syms = {}
+    for e in F + J:
+        for a in e.free_symbols:
+            syms[a.name] = a
+    try:
+        for e in range(nvar):
+            acc = F[e]
+            for k in range(len(J)):
+                if j_eq[k] != e:
+                    continue
+                o = j_off[k]
+                name = fields[j_var[k]] if o == 0 else "%s_%s%d" % (fields[j_var[k]], "m" if o < 0 else "p", abs(o))
+                if name not in syms:
+                    return False
+                acc = acc - J[k] * syms[name]
+            if sp.expand(acc) != 0 and sp.simplify(acc) != 0:
+                return False
+    except Exception:  # noqa: BLE001  (anything unexpected: keep the general form)
+        return False
+    return True
 
 
 def _switch(name, values):
@@ -339,6 +371,7 @@ def _render_header(L, bodies):
     h.append("#define TF_NCONST %d" % L.n_const)
     h.append("#define TF_NNODEPAR %d" % len(L.node_pars))
     h.append("#define TF_USES_X %d" % int(L.uses_x))
+    h.append("#define TF_F_LINEAR %d" % int(getattr(L, "f_is_linear", False)))
     h.append('#include "tf_model_prelude.h"')
     h.append(_switch("tf_j_eq", L.j_eq))
     h.append(_switch("tf_j_var", L.j_var))

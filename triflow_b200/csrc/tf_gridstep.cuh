@@ -1102,7 +1102,7 @@ __device__ __forceinline__ void gs_stage(const Geom& g, const Buf& b, GsCtx& cx,
           {
             TfNodeIn in;
             node_inputs<M>(in, win, m, i, g, b, 0);
-            tf_model_F<FD>(cst, in, fe);
+            tf_model_F_solver<FD>(cst, in, fe);
           }
           double rhs = __dmul_rn(sd.dt, fe[0]);
 #pragma unroll

@@ -557,6 +557,37 @@ __device__ __forceinline__ void node_inputs(TfNodeIn& in, const double (&win)[NF
 #endif
 }
 
+// F as the SOLVER kernels evaluate it.  For a model that is homogeneous linear in the stencil
+// values with uniform coefficients (TF_F_LINEAR, decided symbolically by the code generator:
+// F == sum_k J_k u_k identically; advection-diffusion, heat) it is that sum -- NNZ fused
+// multiply-adds with Jacobian constants that are table look-ups -- instead of the reference's
+// expanded expression (advection-diffusion: 3 instead of 32 fp64 instructions per node and
+// stage).  Same value up to rounding (the terms that cancel are the same); `model.F`
+// (tf_k_eval_F) and the exact-division build keep the reference's operation order.
+#ifndef TF_F_LINEAR
+#define TF_F_LINEAR 0
+#endif
+template <bool FDIV>
+__device__ __forceinline__ void tf_model_F_solver(const double* __restrict__ cst, const TfNodeIn& in,
+                                                  double (&out)[V]) {
+#if TF_F_LINEAR && TF_FAST_DIV
+  double jv[NNZ];
+  tf_model_J<FDIV>(cst, in, jv);
+  bool first[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) { out[e] = 0.0; first[e] = true; }
+#pragma unroll
+  for (int kk = 0; kk < NNZ; ++kk) {
+    const int e = tf_j_eq(kk);
+    const double u = in.w[tf_j_var(kk)][P + tf_j_off(kk)];
+    out[e] = first[e] ? __dmul_rn(jv[kk], u) : __fma_rn(jv[kk], u, out[e]);
+    first[e] = false;
+  }
+#else
+  tf_model_F<FDIV>(cst, in, out);
+#endif
+}
+
 // -------------------------------------------------------------- J -> A rows
 // Rows of A = I - a*J for a node that touches the domain ends, the border (last
 // P nodes) or the padding.  Dynamic indexing on purpose: rare path.
@@ -1395,7 +1426,7 @@ __device__ __forceinline__ void fwd_body(const Geom& g, const Buf& b, const Stag
       if (i < g.N) {
         TfNodeIn in;
         node_inputs<M>(in, win, m, i, g, b, sys);
-        tf_model_F<FD>(cst, in, fe);
+        tf_model_F_solver<FD>(cst, in, fe);
       }
 #pragma unroll
       for (int e = 0; e < V; ++e) {

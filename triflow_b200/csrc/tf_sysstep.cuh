@@ -404,7 +404,7 @@ __device__ __forceinline__ void sys_stage(const Geom& g, const Buf& b, const Buf
       {                                   // padding nodes too (finite fill, rhs zeroed below)
         TfNodeIn in;
         node_inputs<M>(in, win, m, i, g, b, sys);
-        tf_model_F<FD>(cst, in, fe);
+        tf_model_F_solver<FD>(cst, in, fe);
       }
 #pragma unroll
       for (int e = 0; e < V; ++e) {
@@ -584,7 +584,7 @@ __device__ __forceinline__ void sys_stage_rt(const int I, const bool LAST, const
       {                                   // padding nodes too (finite fill, rhs zeroed below)
         TfNodeIn in;
         node_inputs<M>(in, win, m, i, g, b, sys);
-        tf_model_F<FD>(cst, in, fe);
+        tf_model_F_solver<FD>(cst, in, fe);
       }
 #pragma unroll
       for (int e = 0; e < V; ++e) {
