@@ -110,3 +110,21 @@ def test_fast_division_mode_within_one_ulp(tag):
     F, J, F_ref, J_ref = run_case(tag, fast_div=1)
     assert np.max(np.abs(F - F_ref)) <= 1e-13 * np.max(np.abs(F_ref))
     assert abs(J - J_ref).max() <= 1e-13 * abs(J_ref).max()
+
+
+def test_linear_models_are_recognised():
+    """F == sum_k J_k u_k is decided symbolically; only then may the solver kernels use the sum."""
+    from triflow_b200 import codegen, workloads as W
+    from triflow_b200.model import Model
+    want = {"advdiff": True, "heat": True, "coupled": True, "helper": False, "ks": False,
+            "burgers_up1": False, "film": False}
+    for name, lin in want.items():
+        L = codegen.lower(Model(**W.model_args(name), hold_compilation=True))
+        assert L.f_is_linear is lin, name
+        assert ("#define TF_F_LINEAR %d" % int(lin)) in L.header
+    # per-node coefficients: J is not a table of constants any more -> general form
+    m = Model(**W.model_args("advdiff"), hold_compilation=True)
+    assert codegen.lower(m, ("k",)).f_is_linear is False
+    # an affine model (constant source term) is not homogeneous linear
+    src = Model("k * dxxU - c * dxU + 1", "U", ["k", "c"], hold_compilation=True)
+    assert codegen.lower(src).f_is_linear is False
