@@ -384,6 +384,25 @@ def test_exact_division_mode_matches_too():
     assert rel_traj_err(snaps, traj()["ks_2048"]) <= TRAJ_TOL
 
 
+def test_linear_form_of_F_against_the_reference_order():
+    """Homogeneous linear models: the default build evaluates F as sum_k J_k u_k in the solver
+    kernels, the exact build (fast_div=False) in the reference's operation order.  Both against
+    the reference's golden trajectory of the README problem (100 steps), and against each other."""
+    from triflow_b200 import schemes as S, workloads as W
+    from triflow_b200.compiler import make_cuda_compiler
+    from triflow_b200.model import Model
+    c = W.readme(200)
+    c["dt"] = 0.025
+    hook = S.Dirichlet(U=(1.0, 0.0))
+    fast = gmodel("advdiff")
+    exact = Model(**W.model_args("advdiff"), compiler=make_cuda_compiler(fast_div=False))
+    assert fast._cuda.variant(()).lowered.f_is_linear
+    a = run_fixed(fast, S.ROS3PRw(fast, **FX), c, 100, 20, hook=hook)
+    b = run_fixed(exact, S.ROS3PRw(exact, **FX), c, 100, 20, hook=hook)
+    assert rel_traj_err(a, b) <= 1e-11
+    print("linear form of F vs reference order after 100 steps: %.2e" % rel_traj_err(a, b))
+
+
 def test_error_paths():
     from triflow_b200 import schemes as S
     m = gmodel("ks")
