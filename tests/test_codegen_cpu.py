@@ -31,6 +31,9 @@ extern "C" void run(int N, int periodic, const double* fields, const double* npa
     in.x = x[i];
     double f[TF_NVAR]; double jv[TF_NNZ];
     tf_model_F<TF_FAST_DIV != 0>(cst, in, f); tf_model_J<TF_FAST_DIV != 0>(cst, in, jv);
+#if TF_F_SPLIT && defined(TF_TEST_SPLIT)
+    tf_model_Fs<TF_FAST_DIV != 0>(cst, in, f);      // the monomial-collected form instead
+#endif
     for (int e = 0; e < TF_NVAR; ++e) F[i * TF_NVAR + e] = f[e];
     for (int k = 0; k < TF_NNZ; ++k) J[i * TF_NNZ + k] = jv[k];
   }
@@ -40,8 +43,8 @@ extern "C" void run(int N, int periodic, const double* fields, const double* npa
 _CACHE = {}
 
 
-def build(name, node_pars, fast_div):
-    key = (name, node_pars, fast_div)
+def build(name, node_pars, fast_div, split=False):
+    key = (name, node_pars, fast_div, split)
     if key in _CACHE:
         return _CACHE[key]
     m = Model(**W.model_args(name), hold_compilation=True)
@@ -52,18 +55,21 @@ def build(name, node_pars, fast_div):
         f.write(L.header + HARNESS)
     so = os.path.join(d, "m.so")
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC",
-                           "-DTF_FAST_DIV=%d" % fast_div, "-I", CSRC, src, "-o", so])
+                           "-DTF_FAST_DIV=%d" % fast_div, *(["-DTF_TEST_SPLIT"] if split else []),
+                           "-I", CSRC, src, "-o", so])
     lib = ctypes.CDLL(so)
     _CACHE[key] = (m, L, lib)
     return _CACHE[key]
 
 
-def run_case(tag, fast_div=0):
+def run_case(tag, fast_div=0, split=False):
     x, fields, pars, F_ref, J_ref = load_fj(tag)
     name = model_name_of(tag)
     node_pars = tuple(k for k, v in pars.items()
                       if k != "periodic" and np.ndim(v) > 0)
-    m, L, lib = build(name, node_pars, fast_div)
+    m, L, lib = build(name, node_pars, fast_div, split)
+    if split and not L.f_split:
+        pytest.skip("the model keeps the reference's form of F")
     N = x.size
     dx = (x[-1] - x[0]) / (N - 1)
     cst = L.uniform_table(dx, pars, 1)[0]
@@ -110,6 +116,24 @@ def test_fast_division_mode_within_one_ulp(tag):
     F, J, F_ref, J_ref = run_case(tag, fast_div=1)
     assert np.max(np.abs(F - F_ref)) <= 1e-13 * np.max(np.abs(F_ref))
     assert abs(J - J_ref).max() <= 1e-13 * abs(J_ref).max()
+
+
+@pytest.mark.parametrize("tag", [t for t in fj_tags() if model_name_of(t) in (
+    "ks", "burgers_up1", "burgers_up2", "burgers_up3", "kdv", "burgers_central", "helper_dx")])
+def test_monomial_collected_form_of_F(tag):
+    """The form of F the solver kernels use for nonlinear polynomial-like models (one collected,
+    host-evaluated coefficient per monomial of the stencil values) against the reference's golden
+    F: the same function, different rounding.  The bound is the rounding of the terms that
+    cancel: eps x sum of |monomial terms|, far above |F| on fine grids."""
+    F, J, F_ref, J_ref = run_case(tag, fast_div=1, split=True)
+    x, fields, pars, _, _ = load_fj(tag)
+    dx = (x[-1] - x[0]) / (x.size - 1)
+    p = 3 if "up3" in tag else 2
+    mag = max(np.max(np.abs(v)) for v in fields.values())
+    # largest single term of the stencil polynomial: |coefficient| x |u| (x |u| for the products)
+    big = max(1.0, mag) * mag * max(1.0, 6.0 / dx ** 4 if "ks" in tag else 4.0 / dx ** 3)
+    assert np.max(np.abs(F - F_ref)) <= 64 * np.finfo(float).eps * big
+    assert np.max(np.abs(F - F_ref)) <= 1e-9 * np.max(np.abs(F_ref))
 
 
 def test_linear_models_are_recognised():

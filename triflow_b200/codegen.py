@@ -295,6 +295,27 @@ def lower(model, node_pars=()):
         uses_x = uses_x or any("in.x" in ln for ln in lines)
         setattr(out, which + "_printed", src)
 
+    # cheaper form of F for the solver kernels of nonlinear models: linear stencil part with
+    # host-evaluated coefficients + the expanded remainder (adopted when it saves a third)
+    out.f_split = False
+    const_j = stats["J"]["ops"] == 0 and all("in." not in ln for ln in bodies["J"])   # -> linear form
+    split = (_split_linear_part(model, fields, len(model._dep_vars), p)
+             if not node_pars and not const_j else None)
+    if split is not None:
+        try:
+            consts2 = dict(consts)
+            low = _Lowering(arg_kinds, consts2)
+            tree = ast.parse(printed_source(model, split))
+            results = [low.emit(e) for e in tree.body[0].body[-1].value.elts]
+            lines = list(low.lines) + ["out[%d] = %s;" % (i, r) for i, r in enumerate(results)]
+            st = dict(ops=low.n_ops, div=low.n_div, divc=low.n_divc)
+            cost = lambda t: t["ops"] + 3 * t["divc"] + 20 * t["div"]  # noqa: E731
+            if (cost(st) <= 0.67 * cost(stats["F"]) and not any("in.x" in ln for ln in lines)):
+                consts.update(consts2)
+                bodies["Fs"], stats["Fs"], out.f_split = lines, st, True
+        except Exception:  # noqa: BLE001
+            pass
+
     nvar = model._nvar
     kk = np.asarray(model._sparse_indices[0], dtype=int)
     col = kk // nvar
@@ -317,6 +338,8 @@ def lower(model, node_pars=()):
                                 all("in." not in ln for ln in bodies["J"]))
     out.f_is_linear = bool(out.jacobian_is_constant and not model._help_funcs and not uses_x and
                            _f_equals_j_times_u(model, fields, nvar, p, out.j_eq, out.j_var, out.j_off))
+    if out.f_is_linear:
+        out.f_split = False
     out.fields = fields
     out.header = _render_header(out, bodies)
     out.key = hashlib.sha1(out.header.encode()).hexdigest()[:16]
@@ -353,6 +376,51 @@ def _f_equals_j_times_u(model, fields, nvar, p, j_eq, j_var, j_off):
     return True
 
 
+def _split_linear_part(model, fields, ndep, p):
+    """Every equation as a sum over its monomials in the stencil values, each with ONE collected
+    coefficient (kept together for the printer, so that the lowering hoists it to the host):
+    F_e = sum_m c_m * m(u).  The same function as the reference's expanded expression -- which
+    divides every term separately -- with one multiplication per monomial.  Returns the list of
+    expressions, or None."""
+    import sympy as sp
+    F = model.F_array.tolist()
+    syms = {}
+    for e in F:
+        for a in e.free_symbols:
+            syms[a.name] = a
+    us = []
+    for f in fields:
+        for o in range(-p, p + 1):
+            name = f if o == 0 else "%s_%s%d" % (f, "m" if o < 0 else "p", abs(o))
+            if name in syms:
+                us.append(syms[name])
+    if "x" in syms:
+        us.append(syms["x"])
+    if not us:
+        return None
+    out = []
+    try:
+        for e in F:
+            if sp.count_ops(e) > 400:
+                return None
+            groups = {}
+            for term in sp.Add.make_args(sp.expand(e)):
+                coeff, dep = term.as_independent(*us)
+                groups[dep] = groups.get(dep, 0) + coeff
+            parts = []
+            for dep, coeff in groups.items():
+                coeff = sp.together(coeff)
+                if coeff == 0:
+                    continue
+                parts.append(dep if coeff == 1 else sp.UnevaluatedExpr(coeff) * dep)
+            if not parts:
+                return None
+            out.append(sp.Add(*parts))
+    except Exception:  # noqa: BLE001  (anything unexpected: keep the reference's form)
+        return None
+    return out
+
+
 def _switch(name, values):
     cases = "".join(" case %d: return %d;" % (i, v) for i, v in enumerate(values))
     return ("TF_HD constexpr int %s(int k) { switch (k) {%s default: return 0; } }"
@@ -372,11 +440,13 @@ def _render_header(L, bodies):
     h.append("#define TF_NNODEPAR %d" % len(L.node_pars))
     h.append("#define TF_USES_X %d" % int(L.uses_x))
     h.append("#define TF_F_LINEAR %d" % int(getattr(L, "f_is_linear", False)))
+    h.append("#define TF_F_SPLIT %d" % int(getattr(L, "f_split", False)))
     h.append('#include "tf_model_prelude.h"')
     h.append(_switch("tf_j_eq", L.j_eq))
     h.append(_switch("tf_j_var", L.j_var))
     h.append(_switch("tf_j_off", L.j_off))
-    for which, n in (("F", "TF_NVAR"), ("J", "TF_NNZ")):
+    emit = [("F", "TF_NVAR"), ("J", "TF_NNZ")] + ([("Fs", "TF_NVAR")] if getattr(L, "f_split", False) else [])
+    for which, n in emit:
         h.append("template <bool TF_FD> TF_HD TF_INLINE void tf_model_%s(const double* "
                  "TF_RESTRICT cst, const TfNodeIn& in, double (&out)[%s]) {" % (which, n))
         h.append("  (void)cst; (void)in;")

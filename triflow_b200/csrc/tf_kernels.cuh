@@ -567,6 +567,9 @@ __device__ __forceinline__ void node_inputs(TfNodeIn& in, const double (&win)[NF
 #ifndef TF_F_LINEAR
 #define TF_F_LINEAR 0
 #endif
+#ifndef TF_F_SPLIT
+#define TF_F_SPLIT 0
+#endif
 template <bool FDIV>
 __device__ __forceinline__ void tf_model_F_solver(const double* __restrict__ cst, const TfNodeIn& in,
                                                   double (&out)[V]) {
@@ -583,6 +586,10 @@ __device__ __forceinline__ void tf_model_F_solver(const double* __restrict__ cst
     out[e] = first[e] ? __dmul_rn(jv[kk], u) : __fma_rn(jv[kk], u, out[e]);
     first[e] = false;
   }
+#elif TF_F_SPLIT && TF_FAST_DIV && !defined(TF_NO_F_SPLIT)
+  // nonlinear polynomial-like models: the generator's monomial-collected form (one host-evaluated
+  // coefficient per monomial of the stencil values, no division on the device)
+  tf_model_Fs<FDIV>(cst, in, out);
 #else
   tf_model_F<FDIV>(cst, in, out);
 #endif
