@@ -152,3 +152,19 @@ def test_linear_models_are_recognised():
     # an affine model (constant source term) is not homogeneous linear
     src = Model("k * dxxU - c * dxU + 1", "U", ["k", "c"], hold_compilation=True)
     assert codegen.lower(src).f_is_linear is False
+
+
+def test_which_models_get_the_monomial_collected_form():
+    from triflow_b200 import codegen, workloads as W
+    from triflow_b200.model import Model
+    want = {"ks": True, "burgers_up1": True, "kdv": True, "advdiff": False, "heat": False,
+            "film": False, "helper": False}
+    for name, split in want.items():
+        L = codegen.lower(Model(**W.model_args(name), hold_compilation=True))
+        assert L.f_split is split, name
+        assert ("tf_model_Fs" in L.header) is split
+        if split:                                  # no division left on the device, fewer operations
+            assert L.stats["Fs"]["div"] == 0 and L.stats["Fs"]["divc"] == 0
+            assert L.stats["Fs"]["ops"] < L.stats["F"]["ops"] + 3 * L.stats["F"]["divc"]
+    # per-node coefficients keep the reference's form
+    assert codegen.lower(Model(**W.model_args("ks"), hold_compilation=True), ()).f_split
